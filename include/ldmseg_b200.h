@@ -1,0 +1,184 @@
+/*
+ * ldmseg_b200.h -- C ABI of the B200-native LDMSeg sampling hot path.
+ *
+ * The reference (segments-ai/latent-diffusion-segmentation) is pure Python: its hot path has no
+ * FFI of its own, every FLOP is a PyTorch / diffusers library call.  The entry points below are
+ * therefore the operator set that the reference's Python call sites reduce to; each one cites the
+ * reference call site (file:line under /root/reference) whose arithmetic it replaces.  The Python
+ * mirror of `ldmseg.models` / `ldmseg.schedulers` in latent-diffusion-segmentation_b200/ldmseg
+ * binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C types only: device pointers as void* / typed pointers, sizes as int / int64_t,
+ *     the CUDA stream as void* (cudaStream_t).  No torch types.
+ *   - every call is asynchronous on the given stream and returns 0 on success, non-zero on
+ *     failure; ldmseg_last_error_string() describes the failure (thread-local).
+ *   - no call allocates memory that outlives it; the caller owns all buffers.
+ *   - activations are channel-last ("NHWC"): a row-major [rows = n*H*W pixels, C channels] matrix,
+ *     bf16 unless stated; weights are bf16 [N out-channels, K] K-contiguous, K ordered
+ *     [segment][tap ky,kx][channel], each (segment, tap) slice padded to a multiple of 64.
+ */
+#ifndef LDMSEG_B200_H_
+#define LDMSEG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDMSEG_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int ldmseg_version(void);
+const char* ldmseg_last_error_string(void);
+/* Number of kernel launches issued through this library since load (for bench accounting). */
+int64_t ldmseg_launch_count(void);
+
+/* ---- implicit GEMM on tcgen05 (conv3x3 / conv1x1 / linear) ------------------------------ *
+ * Replaces F.conv2d / F.linear inside diffusers ResnetBlock2D, Transformer2DModel, Attention,
+ * FeedForward, Downsample2D, Upsample2D (call sites ldmseg/models/unet.py:357,361-373,388-395,
+ * 401-425,431) and the nn.Conv2d / nn.ConvTranspose2d of GeneralVAESeg.decode
+ * (ldmseg/models/vae.py:133,155,164,267-271).
+ *
+ *   out[m, n] = epilogue( sum_seg sum_tap sum_c  A_seg[pixel(m) + tap, c] * Wt[n, k(seg,tap,c)] )
+ *
+ * Up to LDMSEG_MAX_SRC channel-last sources share the output's spatial geometry (nb, h, w);
+ * a segment reads one source with 1 tap (1x1 / linear) or 9 taps (3x3, zero padding 1).
+ * Several segments accumulate into the same output tile (concat-free skip connections, fused
+ * 1x1 shortcut).  A plain [M, K] matrix is the geometry nb=1, h=1, w=M.
+ */
+#define LDMSEG_MAX_SRC 3
+#define LDMSEG_MAX_SEG 4
+
+enum { LDMSEG_OUT_BF16 = 0, LDMSEG_OUT_F32 = 1 };
+enum { LDMSEG_ACT_NONE = 0, LDMSEG_ACT_SILU = 1, LDMSEG_ACT_GEGLU = 2 };
+
+typedef struct ldmseg_igemm_params {
+  /* A sources */
+  const void* src[LDMSEG_MAX_SRC];   /* bf16 [nb*h*w, src_c[i]] */
+  int src_c[LDMSEG_MAX_SRC];         /* channels (row stride, elements); multiple of 8 */
+  int nsrc;
+  int nb, h, w;                      /* output (= input) geometry; M = nb*h*w */
+  /* K segments, in weight order */
+  int nseg;
+  int seg_src[LDMSEG_MAX_SEG];       /* index into src[] */
+  int seg_taps[LDMSEG_MAX_SEG];      /* 1 or 9 */
+  /* B operand */
+  const void* weight;                /* bf16 [n, ktot] */
+  int n;                             /* output channels */
+  int ktot;                          /* sum over segments of taps * roundup(src_c, 64) */
+  /* epilogue */
+  const float* bias;                 /* [n] or NULL */
+  const float* rowbias;              /* [nb, rowbias_ld] added per image, or NULL */
+  int rowbias_ld;
+  const void* residual;              /* bf16 [M, res_ld] or NULL */
+  int res_ld;
+  void* out;                         /* bf16 or f32 [M, out_ld]; GEGLU writes n/2 columns */
+  int out_ld;
+  int out_dtype;                     /* LDMSEG_OUT_* */
+  int act;                           /* LDMSEG_ACT_* */
+  /* scheduling */
+  int block_n;                       /* 0 = choose; else 64 / 128 / 256 */
+  int split_k;                       /* 0/1 = none; >1 needs workspace */
+  float* workspace;                  /* split-K partials: f32 [M_pad, n_pad] zero-initialised */
+  int* tile_counters;                /* split-K: int32 per output tile, zero-initialised */
+} ldmseg_igemm_params;
+
+int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);
+
+/* Reference-grade CUDA-core version of the same contract (fp32 accumulate, no tensor cores).
+ * Test infrastructure for the tcgen05 kernel -- never on the product path. */
+int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream);
+
+/* ---- normalisation ---------------------------------------------------------------------- *
+ * GroupNorm(32 groups)+optional SiLU over a (virtually concatenated) pair of channel-last
+ * sources; replaces nn.GroupNorm + nn.SiLU in diffusers ResnetBlock2D.norm1/norm2,
+ * Transformer2DModel.norm, UNet conv_norm_out (ldmseg/models/unet.py:428-430) and the GroupNorm
+ * of the seg decoder (ldmseg/models/vae.py:162).  stats is a scratch f32 [nb, groups, 2]. */
+int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int c1, int nb, int hw, int groups,
+                     const float* gamma, const float* beta, float eps, int silu, void* out,
+                     float* stats, void* stream);
+/* LayerNorm over the channel dim of each row (tokens or pixels); replaces nn.LayerNorm in
+ * BasicTransformerBlock.norm1/norm3 and LayerNorm2d (ldmseg/models/vae.py:309-322). */
+int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma, const float* beta,
+                     float eps, int silu, void* out, void* stream);
+
+/* ---- attention -------------------------------------------------------------------------- *
+ * softmax(Q K^T / sqrt(d)) V per (image, head); replaces F.scaled_dot_product_attention in
+ * diffusers AttnProcessor2_0 (self-attention only; cross-attention is removed by
+ * ldmseg/models/unet.py:83-105).  qkv is bf16 [nb*ntok, 3*heads*d] (q | k | v column blocks),
+ * out is bf16 [nb*ntok, heads*d]. */
+int ldmseg_attention(const void* qkv, int nb, int ntok, int heads, int d, void* out, void* stream);
+int ldmseg_attention_simple(const void* qkv, int nb, int ntok, int heads, int d, void* out,
+                            void* stream);
+
+/* ---- element-wise / layout -------------------------------------------------------------- */
+/* h * gelu_erf(g) for x = [rows, 2*c] = (h | g): diffusers GEGLU. */
+int ldmseg_geglu(const void* x, int rows, int c, void* out, void* stream);
+/* nearest x2 upsample of a channel-last bf16 tensor (diffusers Upsample2D). */
+int ldmseg_upsample2x(const void* src, int nb, int h, int w, int c, void* out, void* stream);
+/* im2col for 3x3 stride-2 convs: out [nb*ho*wo, 9*c], taps ordered (ky,kx); pad_lo = zero padding
+ * before (top/left): 1 for the UNet Downsample2D (padding=1), 0 for the VAE encoder
+ * (F.pad(0,1,0,1) then padding=0). */
+int ldmseg_im2col_s2(const void* src, int nb, int h, int w, int c, int pad_lo, void* out,
+                     void* stream);
+/* NCHW f32 -> channel-last bf16 with channel padding (cpad >= c, zeros), optional affine
+ * (y = x*scale + shift) : UNet input / VAE input (2x-1, ldmseg/trainers/trainers_ldm_cond.py:369). */
+int ldmseg_nchw_to_nhwc_bf16(const float* src, int nb, int c, int hw, int cpad, int coff,
+                             float scale, float shift, void* out, void* stream);
+/* channel-last f32 [nb*hw, ld] (first c columns) -> NCHW f32, optional scale. */
+int ldmseg_nhwc_f32_to_nchw(const float* src, int nb, int c, int hw, int ld, float scale,
+                            float* out, void* stream);
+/* channel-last bf16 [nb*hw, ld] -> NCHW f32 */
+int ldmseg_nhwc_bf16_to_nchw(const void* src, int nb, int c, int hw, int ld, float scale,
+                             float* out, void* stream);
+
+/* ---- scheduler -------------------------------------------------------------------------- *
+ * DDIM (eta = 0) update; replaces DDIMNoiseScheduler.step
+ * (ldmseg/schedulers/ddim_scheduler.py:218-269).  All tensors f32, any layout (element-wise).
+ * prediction_type: 0 epsilon, 1 sample, 2 v_prediction.  prev_sample / pred_x0 may be NULL.
+ * Optional ancestral noise (DDPM extension, eta=1): sigma > 0 with noise != NULL. */
+int ldmseg_ddim_step(const float* model_out, const float* sample, int64_t n, float alpha_t,
+                     float alpha_prev, int prediction_type, int clip, float clip_range,
+                     int use_clipped, float sigma, const float* noise, float* prev_sample,
+                     float* pred_x0, void* stream);
+
+/* Fused sampler step used by the CUDA-graph loop (ldmseg/trainers/trainers_ldm_cond.py:1127-1159):
+ * reads eps f32 [M,4] (channel-last conv_out output) and the f32 latent state [M,4]; writes the
+ * new state, x0, and the next UNet input row bf16 [M,16] = (x_{t-1} | rgb | x0 | 0).
+ * The step index is read from device memory (*step_ptr) so one captured graph serves all steps;
+ * coef is f32 [nsteps, 4] = (sqrt_a_t, sqrt_1ma_t, sqrt_a_prev, sqrt_1ma_prev); on the last step
+ * the state becomes x0 (Q1 in SURVEY.md).  Optional inpainting blend (extension): mask f32 [M],
+ * known f32 [M,4] (already noised to t_prev by the caller per step: known[step]). */
+int ldmseg_sampler_step(const float* eps, float* latents, float* x0, const float* rgb_latents,
+                        void* unet_in, int64_t m, const float* coef, const int* step_ptr,
+                        int nsteps, int self_cond, const float* mask, const float* known,
+                        const float* noise, const float* sigma, void* stream);
+int ldmseg_advance_step(int* step_ptr, void* stream);
+
+/* ---- time embedding --------------------------------------------------------------------- *
+ * y[r, :] = act_out( W x_act(r) + b ), f32, small-batch (r = timesteps): Timesteps sinusoid,
+ * TimestepEmbedding and the 22 time_emb_proj linears (ldmseg/models/unet.py:303-307). */
+int ldmseg_timestep_sinusoid(const float* t, int rows, int dim, int flip_sin_to_cos,
+                             float freq_shift, float* out, void* stream);
+int ldmseg_small_linear(const float* x, int rows, int k, const float* w, const float* b, int n,
+                        int silu_in, int silu_out, float* out, int out_ld, void* stream);
+
+/* ---- seg decoder tail ------------------------------------------------------------------- *
+ * ConvTranspose2d(k2,s2) output comes out of ldmseg_igemm as [M, 4*c] (tap-major columns);
+ * this scatters it to the 2x grid and applies LayerNorm2d + SiLU (vae.py:155-157, 309-322). */
+int ldmseg_convt_shuffle_ln(const void* src, int nb, int h, int w, int c, const float* gamma,
+                            const float* beta, float eps, int silu, void* out, void* stream);
+/* bilinear x2 (align_corners=False) of channel-last bf16/f32 logits to NCHW f32 (vae.py:270). */
+int ldmseg_bilinear2x_to_nchw(const void* src, int src_is_f32, int nb, int h, int w, int c, int ld,
+                              float* out, void* stream);
+/* fused fast path: bilinear x2 + argmax + softmax max-prob -> ids u8 [nb, 2h, 2w], prob f32
+ * (ldmseg/trainers/trainers_ldm_cond.py:428-433). */
+int ldmseg_bilinear2x_argmax(const void* src, int src_is_f32, int nb, int h, int w, int c, int ld,
+                             uint8_t* ids, float* maxprob, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDMSEG_B200_H_ */

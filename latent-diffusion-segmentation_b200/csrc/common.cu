@@ -1,0 +1,78 @@
+// Library-level entry points and host helpers (error string, launch counter, TMA encode).
+#include "common.h"
+
+#include <cstring>
+#include <mutex>
+
+#include "../../include/ldmseg_b200.h"
+
+namespace ldm {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // make sure a context exists on the current device
+    cudaFree(nullptr);
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver / no GPU?)");
+    return -3;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+              static_cast<int>(r), rank, (unsigned long long)gdim[0],
+              (unsigned long long)(rank > 1 ? gdim[1] : 0), (unsigned long long)(rank > 2 ? gdim[2] : 0),
+              (unsigned long long)(rank > 3 ? gdim[3] : 0), bdim[0], rank > 1 ? bdim[1] : 0,
+              rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0);
+    return -4;
+  }
+  return 0;
+}
+
+}  // namespace ldm
+
+extern "C" int ldmseg_version(void) { return LDMSEG_ABI_VERSION; }
+extern "C" const char* ldmseg_last_error_string(void) { return ldm::g_err; }
+extern "C" int64_t ldmseg_launch_count(void) {
+  return ldm::g_launch_count.load(std::memory_order_relaxed);
+}

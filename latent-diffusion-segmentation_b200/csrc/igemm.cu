@@ -1,0 +1,611 @@
+// Implicit GEMM on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// One kernel covers every contraction of the UNet / VAE hot path that is not attention:
+// conv3x3 (9 shifted TMA box loads of the channel-last activation, zero padding by TMA
+// out-of-bounds fill), conv1x1 / linear (1 tap), concat-free skip connections and the fused 1x1
+// shortcut (several K segments accumulating into one TMEM tile).
+//
+// Replaces F.conv2d / F.linear inside diffusers' ResnetBlock2D / Transformer2DModel / Attention /
+// FeedForward / Downsample2D / Upsample2D as called from /root/reference/ldmseg/models/unet.py:357,
+// 361-373, 388-395, 401-425, 431, and the convs of GeneralVAESeg.decode (models/vae.py:133-172).
+//
+// CTA = 192 threads, persistent over (tile, k-split) work items:
+//   warp 0      TMA producer   (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5  epilogue: tcgen05.ld -> bias / row-bias / residual / SiLU / GEGLU -> global
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages
+// (tmem_full/tmem_empty) between MMA and epilogue so tile i's epilogue overlaps tile i+1's MMAs.
+//
+// Tile: BLOCK_M = 128 output pixels x BN output channels, BLOCK_K = 64 (one 128-byte swizzle row).
+#include "common.h"
+#include <cstring>
+#include "ptx.cuh"
+#include "../../include/ldmseg_b200.h"
+
+namespace ldm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kIgemmThreads = 192;
+constexpr int kABytes = BM * BK * 2;  // 16 KB per stage
+
+struct alignas(64) IgemmKParams {
+  CUtensorMap a_map[LDMSEG_MAX_SRC];
+  CUtensorMap b_map;
+  int nseg;
+  int seg_src[LDMSEG_MAX_SEG];
+  int seg_taps[LDMSEG_MAX_SEG];
+  int seg_cblocks[LDMSEG_MAX_SEG];
+  int M, N, H, W, HW;
+  int num_m_tiles, num_n_tiles, num_kb;
+  const float* bias;
+  const float* rowbias;
+  int rowbias_ld;
+  const __nv_bfloat16* residual;
+  int res_ld;
+  void* out;
+  int out_ld;
+  int out_f32;
+  int act;
+  int split_k;
+  float* workspace;
+  int ws_ld;
+  int* counters;
+};
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 160) ? 5 : 4;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // stages + barriers (2*stages + 4) * 8 + tmem ptr + split-K flag, + 1024 alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+// Applies the epilogue to 32 consecutive output columns [n, n+32) of row m and stores them.
+__device__ __forceinline__ void epilogue_store32(const IgemmKParams& p, float (&v)[32], int m,
+                                                 int n) {
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+  }
+  if (p.rowbias != nullptr) {
+    const float* rb = p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) v[j] += __ldg(rb + n + j);
+  }
+  if (p.act == LDMSEG_ACT_GEGLU) {
+    // columns come interleaved per 32: [16 x h | 16 x g]; output column = n/2 + i
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = v[i] * gelu_erf_f(v[16 + i]);
+    const int no = n >> 1;
+    if (n < p.N) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                           static_cast<size_t>(m) * p.out_ld + no;
+      uint4 a, b;
+      a.x = pack_bf16x2(o[0], o[1]);
+      a.y = pack_bf16x2(o[2], o[3]);
+      a.z = pack_bf16x2(o[4], o[5]);
+      a.w = pack_bf16x2(o[6], o[7]);
+      b.x = pack_bf16x2(o[8], o[9]);
+      b.y = pack_bf16x2(o[10], o[11]);
+      b.z = pack_bf16x2(o[12], o[13]);
+      b.w = pack_bf16x2(o[14], o[15]);
+      reinterpret_cast<uint4*>(dst)[0] = a;
+      reinterpret_cast<uint4*>(dst)[1] = b;
+    }
+    return;
+  }
+  if (p.residual != nullptr) {
+    const __nv_bfloat16* r = p.residual + static_cast<size_t>(m) * p.res_ld + n;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (n + g * 8 + 8 <= p.N) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + g);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[g * 8 + 0] += f.x; v[g * 8 + 1] += f.y;
+        f = unpack_bf16x2(u.y); v[g * 8 + 2] += f.x; v[g * 8 + 3] += f.y;
+        f = unpack_bf16x2(u.z); v[g * 8 + 4] += f.x; v[g * 8 + 5] += f.y;
+        f = unpack_bf16x2(u.w); v[g * 8 + 6] += f.x; v[g * 8 + 7] += f.y;
+      } else {
+        for (int j = g * 8; j < g * 8 + 8; ++j)
+          if (n + j < p.N) v[j] += __bfloat162float(r[j]);
+      }
+    }
+  }
+  if (p.act == LDMSEG_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+  }
+  if (p.out_f32) {
+    float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (n + g * 4 + 4 <= p.N) {
+        reinterpret_cast<float4*>(dst)[g] =
+            make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      } else {
+        for (int j = g * 4; j < g * 4 + 4; ++j)
+          if (n + j < p.N) dst[j] = v[j];
+      }
+    }
+  } else {
+    __nv_bfloat16* dst =
+        reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + n;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (n + g * 8 + 8 <= p.N) {
+        uint4 u;
+        u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+        u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+        u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+        u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+        reinterpret_cast<uint4*>(dst)[g] = u;
+      } else {
+        for (int j = g * 8; j < g * 8 + 8; ++j)
+          if (n + j < p.N) dst[j] = __float2bfloat16(v[j]);
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_kernel(const __grid_constant__ IgemmKParams p) {
+  using Cfg = IgemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  volatile int* is_last_smem = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.a_map[p.seg_src[s]]);
+    tma_prefetch_desc(&p.b_map);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int total_work = num_tiles * p.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
+        const int tile = wi / p.split_k;
+        const int split = wi - tile * p.split_k;
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * BM;
+        const int x0 = m0 % p.W;
+        const int y0 = (m0 / p.W) % p.H;
+        const int b0 = m0 / p.HW;
+        const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
+        const int kb_end =
+            static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
+        // decode kb_begin -> (segment, tap, channel block)
+        int seg = 0, rem = kb_begin;
+        while (seg < p.nseg - 1 && rem >= p.seg_taps[seg] * p.seg_cblocks[seg]) {
+          rem -= p.seg_taps[seg] * p.seg_cblocks[seg];
+          ++seg;
+        }
+        int tap = rem / p.seg_cblocks[seg];
+        int cb = rem - tap * p.seg_cblocks[seg];
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          int dx = 0, dy = 0;
+          if (p.seg_taps[seg] == 9) {
+            dy = tap / 3 - 1;
+            dx = tap - (tap / 3) * 3 - 1;
+          }
+          tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
+                      cb * BK, x0 + dx, y0 + dy, b0);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK,
+                      n_tile * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++cb == p.seg_cblocks[seg]) {
+            cb = 0;
+            if (++tap == p.seg_taps[seg]) {
+              tap = 0;
+              ++seg;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
+        const int tile = wi / p.split_k;
+        const int split = wi - tile * p.split_k;
+        const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
+        const int kb_end =
+            static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc =
+              make_smem_desc_sw128(smem_u32(smem_a + stage * kABytes), 16, 1024);
+          const uint64_t bdesc =
+              make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int et = threadIdx.x - 64;  // 0..127
+    int it = 0;
+    for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
+      const int tile = wi / p.split_k;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = m_tile * BM + q * 32 + lane;
+      const int n0 = n_tile * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (p.split_k <= 1) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c, r);
+          tmem_wait_ld();
+          if (m < p.M) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_store32(p, v, m, n0 + c);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      } else {
+        // split-K: accumulate the partial tile into the f32 workspace; the last CTA to finish a
+        // tile applies the epilogue and re-zeroes the workspace (ready for the next launch).
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c, r);
+          tmem_wait_ld();
+          if (m < p.M) {
+            float* ws = p.workspace + static_cast<size_t>(m) * p.ws_ld + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < p.N) atomicAdd(ws + j, __uint_as_float(r[j]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const int old = atomicAdd(p.counters + tile, 1);
+          *is_last_smem = (old == p.split_k - 1) ? 1 : 0;
+          if (old == p.split_k - 1) p.counters[tile] = 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int is_last = *is_last_smem;
+        if (is_last) {
+          __threadfence();
+          if (m < p.M) {
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+              if (n0 + c >= p.N) break;
+              float* ws = p.workspace + static_cast<size_t>(m) * p.ws_ld + n0 + c;
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (n0 + c + j < p.N) {
+                  v[j] = __ldcg(ws + j);
+                  ws[j] = 0.f;
+                } else {
+                  v[j] = 0.f;
+                }
+              }
+              epilogue_store32(p, v, m, n0 + c);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reference-grade CUDA-core kernel with the same contract (one thread per output element).
+__global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int ncols = p.n;
+  if (idx >= static_cast<long long>(M) * ncols) return;
+  const int m = static_cast<int>(idx / ncols);
+  const int n = static_cast<int>(idx - static_cast<long long>(m) * ncols);
+  const int x = m % p.w, y = (m / p.w) % p.h, b = m / HW;
+  const __nv_bfloat16* wrow =
+      reinterpret_cast<const __nv_bfloat16*>(p.weight) + static_cast<size_t>(n) * p.ktot;
+  float acc = 0.f;
+  int koff = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    const int src = p.seg_src[s];
+    const int C = p.src_c[src];
+    const int Cpad = (C + 63) / 64 * 64;
+    const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.src[src]);
+    for (int tap = 0; tap < p.seg_taps[s]; ++tap) {
+      int dy = 0, dx = 0;
+      if (p.seg_taps[s] == 9) {
+        dy = tap / 3 - 1;
+        dx = tap % 3 - 1;
+      }
+      const int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
+        const __nv_bfloat16* arow =
+            a + (static_cast<size_t>(b) * HW + static_cast<size_t>(yy) * p.w + xx) * C;
+        for (int c = 0; c < C; ++c)
+          acc += __bfloat162float(arow[c]) * __bfloat162float(wrow[koff + c]);
+      }
+      koff += Cpad;
+    }
+  }
+  // epilogue identical to the tcgen05 kernel (GEGLU handled by the pair thread layout below)
+  if (p.bias) acc += p.bias[n];
+  if (p.rowbias) acc += p.rowbias[static_cast<size_t>(b) * p.rowbias_ld + n];
+  if (p.act == LDMSEG_ACT_GEGLU) {
+    // interleaved [16 h | 16 g] per 32 columns; the g thread combines with its h partner through
+    // a recomputation-free trick: only h threads write, after fetching g via shuffle.
+    const int j = n & 31;
+    const float other = __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (j < 16) {
+      const float o = acc * gelu_erf_f(other);
+      reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + (n >> 5) * 16 +
+                                              j] = __float2bfloat16(o);
+    }
+    return;
+  }
+  if (p.residual)
+    acc += __bfloat162float(
+        reinterpret_cast<const __nv_bfloat16*>(p.residual)[static_cast<size_t>(m) * p.res_ld + n]);
+  if (p.act == LDMSEG_ACT_SILU) acc = silu_f(acc);
+  if (p.out_dtype == LDMSEG_OUT_F32)
+    reinterpret_cast<float*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] = acc;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] =
+        __float2bfloat16(acc);
+}
+
+// ------------------------------------------------------------------------------------------
+static int validate(const ldmseg_igemm_params* p) {
+  LDM_REQUIRE(p != nullptr, "igemm: null params");
+  LDM_REQUIRE(p->nsrc >= 1 && p->nsrc <= LDMSEG_MAX_SRC, "igemm: nsrc out of range");
+  LDM_REQUIRE(p->nseg >= 1 && p->nseg <= LDMSEG_MAX_SEG, "igemm: nseg out of range");
+  LDM_REQUIRE(p->nb > 0 && p->h > 0 && p->w > 0 && p->n > 0, "igemm: bad geometry");
+  const long long hw = static_cast<long long>(p->h) * p->w;
+  if (p->w >= BM) {
+    LDM_REQUIRE(p->w % BM == 0 || (p->h == 1 && p->nb == 1), "igemm: w >= 128 must be a multiple of 128");
+  } else {
+    LDM_REQUIRE(BM % p->w == 0, "igemm: w < 128 must divide 128 (got %d)", p->w);
+    if (hw >= BM)
+      LDM_REQUIRE(hw % BM == 0, "igemm: h*w must be a multiple of 128");
+    else
+      LDM_REQUIRE(BM % hw == 0, "igemm: h*w must divide 128");
+  }
+  int ktot = 0;
+  for (int s = 0; s < p->nseg; ++s) {
+    LDM_REQUIRE(p->seg_src[s] >= 0 && p->seg_src[s] < p->nsrc, "igemm: bad seg_src");
+    LDM_REQUIRE(p->seg_taps[s] == 1 || p->seg_taps[s] == 9, "igemm: taps must be 1 or 9");
+    const int c = p->src_c[p->seg_src[s]];
+    LDM_REQUIRE(c > 0 && c % 8 == 0, "igemm: source channels must be a multiple of 8 (got %d)", c);
+    ktot += p->seg_taps[s] * ((c + BK - 1) / BK * BK);
+  }
+  LDM_REQUIRE(ktot == p->ktot, "igemm: ktot mismatch (expected %d, got %d)", ktot, p->ktot);
+  for (int i = 0; i < p->nsrc; ++i)
+    LDM_REQUIRE(p->src[i] != nullptr && (reinterpret_cast<uintptr_t>(p->src[i]) & 15) == 0,
+                "igemm: source %d null or not 16-byte aligned", i);
+  LDM_REQUIRE(p->weight && (reinterpret_cast<uintptr_t>(p->weight) & 15) == 0,
+              "igemm: weight null or misaligned");
+  LDM_REQUIRE(p->out != nullptr, "igemm: null out");
+  if (p->act == LDMSEG_ACT_GEGLU) {
+    LDM_REQUIRE(p->n % 32 == 0 && p->out_dtype == LDMSEG_OUT_BF16 && p->residual == nullptr,
+                "igemm: GEGLU needs n %% 32 == 0, bf16 out, no residual");
+    LDM_REQUIRE(p->out_ld % 8 == 0, "igemm: GEGLU out_ld must be a multiple of 8");
+  }
+  if (p->out_dtype == LDMSEG_OUT_BF16 && p->act != LDMSEG_ACT_GEGLU)
+    LDM_REQUIRE(p->out_ld % 8 == 0 || p->n < 8, "igemm: bf16 out_ld must be a multiple of 8");
+  if (p->out_dtype == LDMSEG_OUT_F32)
+    LDM_REQUIRE(p->out_ld % 4 == 0, "igemm: f32 out_ld must be a multiple of 4");
+  if (p->residual) LDM_REQUIRE(p->res_ld % 8 == 0, "igemm: res_ld must be a multiple of 8");
+  return 0;
+}
+
+template <int BN>
+static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    configured = true;
+  }
+  igemm_kernel<BN><<<grid, kIgemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  return check_launch("igemm_kernel");
+}
+
+static int choose_block_n(int m_tiles, int n, int sms) {
+  // pick the tile width with the lowest (waves x per-tile MMA time) estimate; ties -> wider
+  const int cands[4] = {256, 160, 128, 64};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const int n_tiles = (n + bn - 1) / bn;
+    const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+    const long long waves = (tiles + sms - 1) / sms;
+    // narrow tiles are smem-bandwidth-bound: never cheaper than a ~96-wide tile
+    const double tile_cost = bn < 96 ? 96.0 : static_cast<double>(bn);
+    const double cost = static_cast<double>(waves) * tile_cost + 8.0;  // + fixed per-wave overhead
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace ldm
+
+using namespace ldm;
+
+extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
+  if (int rc = validate(p)) return rc;
+  IgemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int M = p->nb * p->h * p->w;
+  const int HW = p->h * p->w;
+  // A box: 128 consecutive pixels of the flattened (n, y, x) order
+  uint32_t bw = p->w >= BM ? BM : p->w;
+  uint32_t bh = (p->w >= BM) ? 1 : (HW >= BM ? BM / p->w : p->h);
+  uint32_t bb = BM / (bw * bh);
+  for (int i = 0; i < p->nsrc; ++i) {
+    const uint64_t C = p->src_c[i];
+    uint64_t dims[4] = {C, static_cast<uint64_t>(p->w), static_cast<uint64_t>(p->h),
+                        static_cast<uint64_t>(p->nb)};
+    uint64_t strides[3] = {C * 2, C * 2 * p->w, C * 2 * p->w * p->h};
+    uint32_t box[4] = {BK, bw, bh, bb};
+    if (int rc = encode_tmap_bf16(&kp.a_map[i], p->src[i], 4, dims, strides, box)) return rc;
+  }
+  const int m_tiles = (M + BM - 1) / BM;
+  int bn = p->block_n;
+  if (bn == 0) bn = choose_block_n(m_tiles, p->n, num_sms());
+  LDM_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "igemm: unsupported block_n %d", bn);
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(p->ktot), static_cast<uint64_t>(p->n)};
+    uint64_t strides[1] = {static_cast<uint64_t>(p->ktot) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    if (int rc = encode_tmap_bf16(&kp.b_map, p->weight, 2, dims, strides, box)) return rc;
+  }
+  kp.nseg = p->nseg;
+  int num_kb = 0;
+  for (int s = 0; s < p->nseg; ++s) {
+    kp.seg_src[s] = p->seg_src[s];
+    kp.seg_taps[s] = p->seg_taps[s];
+    kp.seg_cblocks[s] = (p->src_c[p->seg_src[s]] + BK - 1) / BK;
+    num_kb += kp.seg_taps[s] * kp.seg_cblocks[s];
+  }
+  kp.M = M;
+  kp.N = p->n;
+  kp.H = p->h;
+  kp.W = p->w;
+  kp.HW = HW;
+  kp.num_m_tiles = m_tiles;
+  kp.num_n_tiles = (p->n + bn - 1) / bn;
+  kp.num_kb = num_kb;
+  kp.bias = p->bias;
+  kp.rowbias = p->rowbias;
+  kp.rowbias_ld = p->rowbias_ld;
+  kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
+  kp.res_ld = p->res_ld;
+  kp.out = p->out;
+  kp.out_ld = p->out_ld;
+  kp.out_f32 = p->out_dtype == LDMSEG_OUT_F32;
+  kp.act = p->act;
+  kp.split_k = p->split_k > 1 ? p->split_k : 1;
+  if (kp.split_k > num_kb) kp.split_k = num_kb;
+  if (kp.split_k > 1) {
+    LDM_REQUIRE(p->workspace != nullptr && p->tile_counters != nullptr,
+                "igemm: split_k > 1 needs workspace and tile_counters");
+    kp.workspace = p->workspace;
+    kp.ws_ld = (p->n + 3) / 4 * 4;
+    kp.counters = p->tile_counters;
+  }
+  const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
+  const int grid = static_cast<int>(work < num_sms() ? work : num_sms());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch_igemm<64>(kp, grid, st);
+    case 128: return launch_igemm<128>(kp, grid, st);
+    case 160: return launch_igemm<160>(kp, grid, st);
+    default: return launch_igemm<256>(kp, grid, st);
+  }
+}
+
+extern "C" int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream) {
+  if (int rc = validate(p)) return rc;
+  const int M = p->nb * p->h * p->w;
+  const long long total = static_cast<long long>(M) * p->n;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  igemm_simple_kernel<<<static_cast<unsigned>(blocks), threads, 0,
+                        reinterpret_cast<cudaStream_t>(stream)>>>(*p, M, p->h * p->w);
+  return check_launch("igemm_simple_kernel");
+}

@@ -1,0 +1,273 @@
+"""ctypes binding of libldmseg_b200.so (the C ABI declared in include/ldmseg_b200.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails, a RuntimeError is
+raised.  torch tensors are used only as device-memory handles (data_ptr) and for the current
+stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libldmseg_b200.so")
+
+MAX_SRC = 3
+MAX_SEG = 4
+OUT_BF16, OUT_F32 = 0, 1
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+
+EXPORTS = [
+    "ldmseg_version", "ldmseg_last_error_string", "ldmseg_launch_count", "ldmseg_igemm",
+    "ldmseg_igemm_simple", "ldmseg_groupnorm", "ldmseg_layernorm", "ldmseg_attention",
+    "ldmseg_attention_simple", "ldmseg_geglu", "ldmseg_upsample2x", "ldmseg_im2col_s2",
+    "ldmseg_nchw_to_nhwc_bf16", "ldmseg_nhwc_f32_to_nchw", "ldmseg_nhwc_bf16_to_nchw",
+    "ldmseg_ddim_step", "ldmseg_sampler_step", "ldmseg_advance_step", "ldmseg_timestep_sinusoid",
+    "ldmseg_small_linear", "ldmseg_convt_shuffle_ln", "ldmseg_bilinear2x_to_nchw",
+    "ldmseg_bilinear2x_argmax",
+]
+
+
+class IgemmParams(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * MAX_SRC),
+        ("src_c", C.c_int * MAX_SRC),
+        ("nsrc", C.c_int),
+        ("nb", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("nseg", C.c_int),
+        ("seg_src", C.c_int * MAX_SEG),
+        ("seg_taps", C.c_int * MAX_SEG),
+        ("weight", C.c_void_p),
+        ("n", C.c_int),
+        ("ktot", C.c_int),
+        ("bias", C.c_void_p),
+        ("rowbias", C.c_void_p),
+        ("rowbias_ld", C.c_int),
+        ("residual", C.c_void_p),
+        ("res_ld", C.c_int),
+        ("out", C.c_void_p),
+        ("out_ld", C.c_int),
+        ("out_dtype", C.c_int),
+        ("act", C.c_int),
+        ("block_n", C.c_int),
+        ("split_k", C.c_int),
+        ("workspace", C.c_void_p),
+        ("tile_counters", C.c_void_p),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed to load / resolve symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+            "(there is no CPU fallback for the sampling hot path)")
+    lib = C.CDLL(_LIB_PATH)
+    lib.ldmseg_version.restype = C.c_int
+    lib.ldmseg_last_error_string.restype = C.c_char_p
+    lib.ldmseg_launch_count.restype = C.c_int64
+    vp, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+    sig = {
+        "ldmseg_igemm": [C.POINTER(IgemmParams), vp],
+        "ldmseg_igemm_simple": [C.POINTER(IgemmParams), vp],
+        "ldmseg_groupnorm": [vp, i32, vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, vp],
+        "ldmseg_layernorm": [vp, i32, i32, vp, vp, f32, i32, vp, vp],
+        "ldmseg_attention": [vp, i32, i32, i32, i32, vp, vp],
+        "ldmseg_attention_simple": [vp, i32, i32, i32, i32, vp, vp],
+        "ldmseg_geglu": [vp, i32, i32, vp, vp],
+        "ldmseg_upsample2x": [vp, i32, i32, i32, i32, vp, vp],
+        "ldmseg_im2col_s2": [vp, i32, i32, i32, i32, i32, vp, vp],
+        "ldmseg_nchw_to_nhwc_bf16": [vp, i32, i32, i32, i32, i32, f32, f32, vp, vp],
+        "ldmseg_nhwc_f32_to_nchw": [vp, i32, i32, i32, i32, f32, vp, vp],
+        "ldmseg_nhwc_bf16_to_nchw": [vp, i32, i32, i32, i32, f32, vp, vp],
+        "ldmseg_ddim_step": [vp, vp, i64, f32, f32, i32, i32, f32, i32, f32, vp, vp, vp, vp],
+        "ldmseg_sampler_step": [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp],
+        "ldmseg_advance_step": [vp, vp],
+        "ldmseg_timestep_sinusoid": [vp, i32, i32, i32, f32, vp, vp],
+        "ldmseg_small_linear": [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp],
+        "ldmseg_convt_shuffle_ln": [vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp],
+        "ldmseg_bilinear2x_to_nchw": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
+        "ldmseg_bilinear2x_argmax": [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ldmseg_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "ldmseg_b200: the sampling hot path runs only on CUDA (sm_100a); got a CPU tensor. "
+                "There is deliberately no CPU fallback.")
+
+
+def launch_count() -> int:
+    return int(load().ldmseg_launch_count())
+
+
+# --------------------------------------------------------------------------------------------
+def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: int, h: int, w: int,
+                      segs: Sequence[tuple], weight: torch.Tensor, n: int, out: torch.Tensor,
+                      out_ld: int, *, bias: Optional[torch.Tensor] = None,
+                      rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
+                      residual: Optional[torch.Tensor] = None, res_ld: int = 0, act: int = ACT_NONE,
+                      block_n: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
+                      counters: Optional[torch.Tensor] = None) -> IgemmParams:
+    p = IgemmParams()
+    for i, s in enumerate(srcs):
+        p.src[i] = s.data_ptr()
+        p.src_c[i] = int(src_c[i])
+    p.nsrc = len(srcs)
+    p.nb, p.h, p.w = nb, h, w
+    p.nseg = len(segs)
+    ktot = 0
+    for i, (si, taps) in enumerate(segs):
+        p.seg_src[i] = si
+        p.seg_taps[i] = taps
+        ktot += taps * ((src_c[si] + 63) // 64 * 64)
+    p.weight = weight.data_ptr()
+    p.n = n
+    p.ktot = ktot
+    assert weight.numel() >= n * ktot, (weight.shape, n, ktot)
+    p.bias = _ptr(bias)
+    p.rowbias = _ptr(rowbias)
+    p.rowbias_ld = rowbias_ld
+    p.residual = _ptr(residual)
+    p.res_ld = res_ld
+    p.out = out.data_ptr()
+    p.out_ld = out_ld
+    p.out_dtype = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
+    p.act = act
+    p.block_n = block_n
+    p.split_k = split_k
+    p.workspace = _ptr(workspace)
+    p.tile_counters = _ptr(counters)
+    return p
+
+
+def igemm(p: IgemmParams, simple: bool = False) -> None:
+    lib = load()
+    fn = lib.ldmseg_igemm_simple if simple else lib.ldmseg_igemm
+    _check(fn(C.byref(p), _stream()), "ldmseg_igemm")
+
+
+def groupnorm(src0, c0, src1, c1, nb, hw, groups, gamma, beta, eps, silu, out, stats) -> None:
+    _check(load().ldmseg_groupnorm(_ptr(src0), c0, _ptr(src1), c1, nb, hw, groups, _ptr(gamma),
+                                   _ptr(beta), eps, int(silu), _ptr(out), _ptr(stats), _stream()),
+           "ldmseg_groupnorm")
+
+
+def layernorm(src, rows, c, gamma, beta, eps, silu, out) -> None:
+    _check(load().ldmseg_layernorm(_ptr(src), rows, c, _ptr(gamma), _ptr(beta), eps, int(silu),
+                                   _ptr(out), _stream()), "ldmseg_layernorm")
+
+
+def attention(qkv, nb, ntok, heads, d, out, simple: bool = False) -> None:
+    lib = load()
+    fn = lib.ldmseg_attention_simple if simple else lib.ldmseg_attention
+    _check(fn(_ptr(qkv), nb, ntok, heads, d, _ptr(out), _stream()), "ldmseg_attention")
+
+
+def geglu(x, rows, c, out) -> None:
+    _check(load().ldmseg_geglu(_ptr(x), rows, c, _ptr(out), _stream()), "ldmseg_geglu")
+
+
+def upsample2x(src, nb, h, w, c, out) -> None:
+    _check(load().ldmseg_upsample2x(_ptr(src), nb, h, w, c, _ptr(out), _stream()), "ldmseg_upsample2x")
+
+
+def im2col_s2(src, nb, h, w, c, pad_lo, out) -> None:
+    _check(load().ldmseg_im2col_s2(_ptr(src), nb, h, w, c, pad_lo, _ptr(out), _stream()),
+           "ldmseg_im2col_s2")
+
+
+def nchw_to_nhwc_bf16(src, nb, c, hw, cpad, coff, scale, shift, out) -> None:
+    _check(load().ldmseg_nchw_to_nhwc_bf16(_ptr(src), nb, c, hw, cpad, coff, scale, shift, _ptr(out),
+                                           _stream()), "ldmseg_nchw_to_nhwc_bf16")
+
+
+def nhwc_f32_to_nchw(src, nb, c, hw, ld, scale, out) -> None:
+    _check(load().ldmseg_nhwc_f32_to_nchw(_ptr(src), nb, c, hw, ld, scale, _ptr(out), _stream()),
+           "ldmseg_nhwc_f32_to_nchw")
+
+
+def nhwc_bf16_to_nchw(src, nb, c, hw, ld, scale, out) -> None:
+    _check(load().ldmseg_nhwc_bf16_to_nchw(_ptr(src), nb, c, hw, ld, scale, _ptr(out), _stream()),
+           "ldmseg_nhwc_bf16_to_nchw")
+
+
+def ddim_step(model_out, sample, alpha_t, alpha_prev, ptype, clip, clip_range, use_clipped, prev, x0,
+              sigma: float = 0.0, noise=None) -> None:
+    _check(load().ldmseg_ddim_step(_ptr(model_out), _ptr(sample), model_out.numel(), alpha_t,
+                                   alpha_prev, ptype, int(clip), clip_range, int(use_clipped), sigma,
+                                   _ptr(noise), _ptr(prev), _ptr(x0), _stream()), "ldmseg_ddim_step")
+
+
+def sampler_step(eps, latents, x0, rgb, unet_in, m, coef, step_ptr, nsteps, self_cond, mask=None,
+                 known=None, noise=None, sigma=None) -> None:
+    _check(load().ldmseg_sampler_step(_ptr(eps), _ptr(latents), _ptr(x0), _ptr(rgb), _ptr(unet_in), m,
+                                      _ptr(coef), _ptr(step_ptr), nsteps, int(self_cond), _ptr(mask),
+                                      _ptr(known), _ptr(noise), _ptr(sigma), _stream()),
+           "ldmseg_sampler_step")
+
+
+def advance_step(step_ptr) -> None:
+    _check(load().ldmseg_advance_step(_ptr(step_ptr), _stream()), "ldmseg_advance_step")
+
+
+def timestep_sinusoid(t, rows, dim, flip, freq_shift, out) -> None:
+    _check(load().ldmseg_timestep_sinusoid(_ptr(t), rows, dim, int(flip), freq_shift, _ptr(out),
+                                           _stream()), "ldmseg_timestep_sinusoid")
+
+
+def small_linear(x, rows, k, w, b, n, silu_in, silu_out, out, out_ld) -> None:
+    _check(load().ldmseg_small_linear(_ptr(x), rows, k, _ptr(w), _ptr(b), n, int(silu_in),
+                                      int(silu_out), _ptr(out), out_ld, _stream()),
+           "ldmseg_small_linear")
+
+
+def convt_shuffle_ln(src, nb, h, w, c, gamma, beta, eps, silu, out) -> None:
+    _check(load().ldmseg_convt_shuffle_ln(_ptr(src), nb, h, w, c, _ptr(gamma), _ptr(beta), eps,
+                                          int(silu), _ptr(out), _stream()), "ldmseg_convt_shuffle_ln")
+
+
+def bilinear2x_to_nchw(src, nb, h, w, c, ld, out) -> None:
+    _check(load().ldmseg_bilinear2x_to_nchw(_ptr(src), int(src.dtype == torch.float32), nb, h, w, c,
+                                            ld, _ptr(out), _stream()), "ldmseg_bilinear2x_to_nchw")
+
+
+def bilinear2x_argmax(src, nb, h, w, c, ld, ids, maxprob=None) -> None:
+    _check(load().ldmseg_bilinear2x_argmax(_ptr(src), int(src.dtype == torch.float32), nb, h, w, c,
+                                           ld, _ptr(ids), _ptr(maxprob), _stream()),
+           "ldmseg_bilinear2x_argmax")

@@ -1,0 +1,83 @@
+"""Weight packing for the tcgen05 implicit-GEMM kernel.
+
+The kernel consumes bf16 weights [N, Ktot], K-contiguous, K ordered [segment][tap (ky,kx)][channel]
+with every (segment, tap) slice zero-padded to a multiple of 64 channels (one 128-byte swizzle row
+of the TMA box).  These helpers turn PyTorch-layout parameters into that layout once, at load time.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """[N, C, 3, 3] -> [N, 9 * pad64(C)] (tap-major, then channel)."""
+    n, c, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    cp = _pad64(c)
+    out = torch.zeros(n, 9, cp, dtype=torch.float32, device=w.device)
+    out[:, :, :c] = w.float().permute(0, 2, 3, 1).reshape(n, 9, c)
+    return out.reshape(n, 9 * cp)
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] (or [N, K, 1, 1]) -> [N, pad64(K)]."""
+    if w.dim() == 4:
+        w = w[:, :, 0, 0]
+    n, k = w.shape
+    kp = _pad64(k)
+    out = torch.zeros(n, kp, dtype=torch.float32, device=w.device)
+    out[:, :k] = w.float()
+    return out
+
+
+def split_linear_k(w: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
+    """Linear / 1x1 weight whose K axis is a concat of sources: pad each source slice to 64."""
+    if w.dim() == 4:
+        w = w[:, :, 0, 0]
+    parts, off = [], 0
+    for c in splits:
+        parts.append(pack_linear(w[:, off:off + c]))
+        off += c
+    assert off == w.shape[1]
+    return torch.cat(parts, dim=1)
+
+
+def split_conv3x3_k(w: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
+    """conv3x3 weight over a channel concat: one 9-tap segment per source."""
+    parts, off = [], 0
+    for c in splits:
+        parts.append(pack_conv3x3(w[:, off:off + c]))
+        off += c
+    assert off == w.shape[1]
+    return torch.cat(parts, dim=1)
+
+
+def interleave_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU projection [2*F, K] (h rows then g rows) -> rows interleaved in blocks of 16 so that
+    every 32-column chunk of the GEMM output holds [16 h | 16 g] for the same 16 outputs."""
+    f = w.shape[0] // 2
+    assert f % 16 == 0
+    wh, wg = w[:f].reshape(f // 16, 16, -1), w[f:].reshape(f // 16, 16, -1)
+    wi = torch.cat([wh, wg], dim=1).reshape(2 * f, -1)
+    bh, bg = b[:f].reshape(f // 16, 16), b[f:].reshape(f // 16, 16)
+    bi = torch.cat([bh, bg], dim=1).reshape(2 * f)
+    return wi, bi
+
+
+def pack_convT2x2(w: torch.Tensor, b: torch.Tensor):
+    """ConvTranspose2d(k=2, s=2) weight [Cin, Cout, 2, 2] -> GEMM weight [4*Cout, pad64(Cin)] with
+    row block t = ky*2+kx, and the bias repeated per tap."""
+    cin, cout, kh, kw = w.shape
+    assert kh == 2 and kw == 2
+    wt = w.float().permute(2, 3, 1, 0).reshape(4 * cout, cin)
+    return pack_linear(wt), b.float().repeat(4)
+
+
+def to_bf16(w: torch.Tensor) -> torch.Tensor:
+    return w.to(torch.bfloat16).contiguous()

@@ -1,0 +1,319 @@
+"""Per-kernel numerical checks on a real B200 (run under gpurun).  Each group runs in its own
+process (a device trap in one kernel must not hide the others):
+
+    python tools/kernel_check.py            # all groups, each in a subprocess with a timeout
+    python tools/kernel_check.py --group igemm
+"""
+import argparse
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
+
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "norm", "attn_simple",
+          "attn", "elementwise"]
+
+
+def report(name, got, ref, tol):
+    import torch
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    rel = (got - ref).norm().item() / (ref.norm().item() + 1e-12)
+    bad = not (rel <= tol) or not torch.isfinite(got).all().item()
+    print(f"{'FAIL' if bad else 'PASS'} {name:58s} max_abs={err:.4e} ref_max={scale:.3e} rel_l2={rel:.3e}",
+          flush=True)
+    return not bad
+
+
+def run_group(group):
+    import torch
+    import torch.nn.functional as F
+    from ldmseg import _native as nat
+    from ldmseg import _pack as pk
+
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    bf = torch.bfloat16
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, device=dev) * scale).to(bf)
+
+    def conv_case(name, nb, h, w, cin, cout, *, taps=9, bias=True, residual=False, rowbias=False,
+                  act=nat.ACT_NONE, out_f32=False, block_n=0, split_k=0, simple=False, extra_src=None,
+                  shortcut=False):
+        """out = conv(x (+ extra_src concat)) [+ 1x1 shortcut of the raw sources] ..."""
+        nonlocal ok
+        srcs_c = [cin] + ([extra_src] if extra_src else [])
+        xs = [rnd(nb * h * w, c) for c in srcs_c]
+        ctot = sum(srcs_c)
+        kscale = 1.0 / (ctot * taps) ** 0.5
+        if taps == 9:
+            wt = torch.randn(cout, ctot, 3, 3, device=dev) * kscale
+            packed = pk.split_conv3x3_k(wt, srcs_c)
+        else:
+            wt = torch.randn(cout, ctot, device=dev) * kscale
+            packed = pk.split_linear_k(wt, srcs_c)
+        segs = [(i, taps) for i in range(len(srcs_c))]
+        srcs, src_cs = list(xs), list(srcs_c)
+        wsc = None
+        if shortcut:
+            # extra 1x1 segments over two more raw sources
+            sc_c = [cin]
+            sc_x = [rnd(nb * h * w, c) for c in sc_c]
+            wsc = torch.randn(cout, sum(sc_c), device=dev) / sum(sc_c) ** 0.5
+            packed = torch.cat([packed, pk.split_linear_k(wsc, sc_c)], dim=1)
+            for x_, c_ in zip(sc_x, sc_c):
+                srcs.append(x_)
+                src_cs.append(c_)
+                segs.append((len(srcs) - 1, 1))
+        wb = pk.to_bf16(packed)
+        b = torch.randn(cout, device=dev) if bias else None
+        rb = torch.randn(nb, cout, device=dev) if rowbias else None
+        n_out = cout // 2 if act == nat.ACT_GEGLU else cout
+        res = rnd(nb * h * w, cout) if residual else None
+        out = torch.full((nb * h * w, n_out), float("nan"), device=dev,
+                         dtype=torch.float32 if out_f32 else bf)
+        ws = cnt = None
+        if split_k > 1:
+            ws = torch.zeros((nb * h * w + 128) * ((cout + 3) // 4 * 4), device=dev)
+            cnt = torch.zeros(4096, device=dev, dtype=torch.int32)
+        p = nat.make_igemm_params(srcs, src_cs, nb, h, w, segs, wb, cout, out, n_out, bias=b,
+                                  rowbias=rb, rowbias_ld=cout, residual=res, res_ld=cout, act=act,
+                                  block_n=block_n, split_k=split_k, workspace=ws, counters=cnt)
+        nat.igemm(p, simple=simple)
+        if split_k > 1:  # second launch must see a clean (self-zeroed) workspace
+            nat.igemm(p, simple=simple)
+        torch.cuda.synchronize()
+        # reference in fp32 from the bf16-rounded operands
+        xcat = torch.cat([x.float() for x in xs], dim=1)
+        wq = wt.to(bf).float()
+        if taps == 9:
+            xi = xcat.reshape(nb, h, w, ctot).permute(0, 3, 1, 2)
+            ref = F.conv2d(xi, wq, padding=1).permute(0, 2, 3, 1).reshape(nb * h * w, cout)
+        else:
+            ref = xcat @ wq.t()
+        if shortcut:
+            ref = ref + torch.cat([x.float() for x in srcs[len(xs):]], dim=1) @ wsc.to(bf).float().t()
+        if bias:
+            ref = ref + b
+        if rowbias:
+            ref = ref + rb.repeat_interleave(h * w, dim=0)
+        if act == nat.ACT_GEGLU:
+            r = ref.reshape(nb * h * w, cout // 32, 2, 16)
+            ref = (r[:, :, 0] * F.gelu(r[:, :, 1])).reshape(nb * h * w, cout // 2)
+        if residual:
+            ref = ref + res.float()
+        if act == nat.ACT_SILU:
+            ref = F.silu(ref)
+        ok &= report(name, out, ref, 1e-2 if not out_f32 else 5e-3)
+        if split_k > 1:
+            ok &= report(name + " [ws clean]", ws, torch.zeros_like(ws), 0.0)
+
+    if group == "simple":
+        conv_case("simple linear 256x320->320", 1, 1, 256, 320, 320, taps=1, simple=True)
+        conv_case("simple conv3x3 16x16 64->64", 1, 16, 16, 64, 64, simple=True)
+        conv_case("simple conv3x3 2x8x8 128->64 +res+rowbias silu", 2, 8, 8, 128, 64, residual=True,
+                  rowbias=True, act=nat.ACT_SILU, simple=True)
+        conv_case("simple linear geglu 128x64->128", 1, 1, 128, 64, 128, taps=1, act=nat.ACT_GEGLU,
+                  simple=True)
+        conv_case("simple conv3x3 dual-source + shortcut", 1, 16, 16, 64, 64, extra_src=128,
+                  shortcut=True, simple=True)
+    elif group == "igemm_plain":
+        for bn in (64, 128, 160, 256):
+            conv_case(f"igemm linear 4096x320->640 bn={bn}", 1, 1, 4096, 320, 640, taps=1, block_n=bn)
+        conv_case("igemm linear 4096x320->320 auto", 1, 1, 4096, 320, 320, taps=1)
+        conv_case("igemm linear 64x1280->1280 (M<128)", 1, 1, 64, 1280, 1280, taps=1)
+        conv_case("igemm linear 8192x1280->5120 f32 bias", 1, 1, 8192, 1280, 5120, taps=1, out_f32=True)
+        conv_case("igemm linear 256x24->8 (K,N tiny)", 1, 1, 256, 24, 8, taps=1)
+    elif group == "igemm_conv":
+        conv_case("igemm conv3x3 1x64x64 320->320", 1, 64, 64, 320, 320)
+        conv_case("igemm conv3x3 2x32x32 640->640", 2, 32, 32, 640, 640)
+        conv_case("igemm conv3x3 1x16x16 1280->1280", 1, 16, 16, 1280, 1280)
+        conv_case("igemm conv3x3 1x8x8 1280->1280 (M=64)", 1, 8, 8, 1280, 1280)
+        conv_case("igemm conv3x3 3x8x8 1280->640 (odd nb)", 3, 8, 8, 1280, 640)
+        conv_case("igemm conv3x3 1x64x64 16->320 (conv_in)", 1, 64, 64, 16, 320)
+        conv_case("igemm conv3x3 1x64x64 320->4 f32 (conv_out)", 1, 64, 64, 320, 4, out_f32=True)
+        conv_case("igemm conv3x3 1x128x128 64->64", 1, 128, 128, 64, 64)
+        conv_case("igemm conv3x3 1x256x256 64->128", 1, 256, 256, 64, 128)
+    elif group == "igemm_epi":
+        conv_case("igemm conv3x3 +res +rowbias", 2, 32, 32, 320, 320, residual=True, rowbias=True)
+        conv_case("igemm conv3x3 silu", 1, 32, 32, 128, 256, act=nat.ACT_SILU)
+        conv_case("igemm linear geglu 1024x640->5120", 1, 1, 1024, 640, 5120, taps=1, act=nat.ACT_GEGLU)
+        conv_case("igemm conv3x3 dual-source 1280+640->1280", 1, 16, 16, 1280, 1280, extra_src=640)
+        conv_case("igemm conv3x3 dual + 1x1 shortcut", 1, 32, 32, 640, 640, extra_src=320, shortcut=True,
+                  residual=False)
+    elif group == "igemm_splitk":
+        conv_case("igemm conv3x3 1x8x8 1280->1280 split4", 1, 8, 8, 1280, 1280, split_k=4)
+        conv_case("igemm conv3x3 1x16x16 1280->1280 split8 +res", 1, 16, 16, 1280, 1280, split_k=8,
+                  residual=True)
+        conv_case("igemm linear 256x1280->1280 split3 silu", 1, 1, 256, 1280, 1280, taps=1, split_k=3,
+                  act=nat.ACT_SILU)
+    elif group == "norm":
+        for (nb, hw, c0, c1) in [(1, 4096, 320, 0), (2, 1024, 640, 320), (1, 256, 1280, 640),
+                                 (2, 64, 1280, 1280), (1, 65536, 256, 0)]:
+            C = c0 + c1
+            x0 = rnd(nb * hw, c0) + 0.5
+            x1 = rnd(nb * hw, c1, scale=2.0) if c1 else None
+            g = torch.randn(C, device=dev)
+            be = torch.randn(C, device=dev)
+            out = torch.empty(nb * hw, C, device=dev, dtype=bf)
+            stats = torch.empty(nb * 32 * 2, device=dev)
+            nat.groupnorm(x0, c0, x1, c1, nb, hw, 32, g, be, 1e-5, True, out, stats)
+            torch.cuda.synchronize()
+            xc = torch.cat([x0.float()] + ([x1.float()] if c1 else []), dim=1)
+            xi = xc.reshape(nb, hw, C).permute(0, 2, 1)
+            ref = F.silu(F.group_norm(xi, 32, g, be, 1e-5)).permute(0, 2, 1).reshape(nb * hw, C)
+            ok &= report(f"groupnorm+silu nb={nb} hw={hw} c={c0}+{c1}", out, ref, 1e-2)
+        for (rows, c) in [(4096, 320), (1024, 640), (300, 1280), (1000, 256)]:
+            x = rnd(rows, c) + 0.3
+            g = torch.randn(c, device=dev)
+            be = torch.randn(c, device=dev)
+            out = torch.empty(rows, c, device=dev, dtype=bf)
+            nat.layernorm(x, rows, c, g, be, 1e-5, False, out)
+            torch.cuda.synchronize()
+            ok &= report(f"layernorm rows={rows} c={c}", out, F.layer_norm(x.float(), (c,), g, be, 1e-5),
+                         1e-2)
+    elif group in ("attn_simple", "attn"):
+        simple = group == "attn_simple"
+        cases = [(1, 256, 8, 40), (2, 64, 8, 160), (1, 256, 8, 160), (1, 1024, 8, 80),
+                 (1, 4096, 8, 40), (2, 1024, 4, 40)]
+        for (nb, ntok, heads, d) in cases:
+            C = heads * d
+            qkv = rnd(nb * ntok, 3 * C, scale=1.5)
+            out = torch.full((nb * ntok, C), float("nan"), device=dev, dtype=bf)
+            nat.attention(qkv, nb, ntok, heads, d, out, simple=simple)
+            torch.cuda.synchronize()
+            q, k, v = qkv.float().reshape(nb, ntok, 3, heads, d).permute(2, 0, 3, 1, 4)
+            ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(nb * ntok, C)
+            ok &= report(f"{group} nb={nb} ntok={ntok} heads={heads} d={d}", out, ref, 2e-2)
+    elif group == "elementwise":
+        x = rnd(1000, 2 * 640)
+        out = torch.empty(1000, 640, device=dev, dtype=bf)
+        nat.geglu(x, 1000, 640, out)
+        ref = x.float()[:, :640] * F.gelu(x.float()[:, 640:])
+        ok &= report("geglu", out, ref, 1e-2)
+        x = rnd(2 * 16 * 16, 64)
+        out = torch.empty(2 * 32 * 32, 64, device=dev, dtype=bf)
+        nat.upsample2x(x, 2, 16, 16, 64, out)
+        ref = F.interpolate(x.float().reshape(2, 16, 16, 64).permute(0, 3, 1, 2), scale_factor=2.0,
+                            mode="nearest").permute(0, 2, 3, 1).reshape(-1, 64)
+        ok &= report("upsample2x", out, ref, 0.0)
+        for pad_lo in (1, 0):
+            x = rnd(2 * 16 * 16, 64)
+            out = torch.empty(2 * 8 * 8, 9 * 64, device=dev, dtype=bf)
+            nat.im2col_s2(x, 2, 16, 16, 64, pad_lo, out)
+            xi = x.float().reshape(2, 16, 16, 64).permute(0, 3, 1, 2)
+            xi = F.pad(xi, (1, 1, 1, 1)) if pad_lo == 1 else F.pad(xi, (0, 1, 0, 1))
+            cols = F.unfold(xi, 3, stride=2)  # [nb, C*9, L] with C-major, tap-minor
+            L = cols.shape[-1]
+            ref = cols.reshape(2, 64, 9, L).permute(0, 3, 2, 1).reshape(2 * L, 9 * 64)
+            ok &= report(f"im2col_s2 pad_lo={pad_lo}", out, ref, 0.0)
+        src = torch.randn(2, 4, 64 * 64, device=dev)
+        out = torch.zeros(2 * 64 * 64, 16, device=dev, dtype=bf)
+        nat.nchw_to_nhwc_bf16(src, 2, 4, 64 * 64, 16, 4, 2.0, -1.0, out)
+        ref = torch.zeros(2 * 64 * 64, 16, device=dev)
+        ref[:, 4:8] = (src * 2 - 1).permute(0, 2, 1).reshape(-1, 4)
+        ok &= report("nchw_to_nhwc_bf16", out, ref.to(bf), 0.0)
+        src = torch.randn(2 * 4096, 4, device=dev)
+        out = torch.empty(2, 4, 4096, device=dev)
+        nat.nhwc_f32_to_nchw(src, 2, 4, 4096, 4, 0.5, out)
+        ok &= report("nhwc_f32_to_nchw", out, src.reshape(2, 4096, 4).permute(0, 2, 1) * 0.5, 1e-7)
+        # ddim step (all prediction types)
+        for ptype in (0, 1, 2):
+            mo = torch.randn(2, 4, 64, 64, device=dev)
+            xs = torch.randn(2, 4, 64, 64, device=dev)
+            prev = torch.empty_like(mo)
+            x0 = torch.empty_like(mo)
+            a_t, a_p = 0.0059128, 0.0046601
+            nat.ddim_step(mo, xs, a_t, a_p, ptype, False, 1.0, False, prev, x0)
+            at = torch.tensor(a_t)
+            ap = torch.tensor(a_p)
+            bt = 1 - at
+            if ptype == 0:
+                r0 = (xs - bt ** 0.5 * mo) / at ** 0.5
+                eps = mo
+            elif ptype == 1:
+                r0 = mo
+                eps = (xs - at ** 0.5 * r0) / bt ** 0.5
+            else:
+                r0 = at ** 0.5 * xs - bt ** 0.5 * mo
+                eps = at ** 0.5 * mo + bt ** 0.5 * xs
+            rp = ap ** 0.5 * r0 + (1 - ap) ** 0.5 * eps
+            ok &= report(f"ddim_step ptype={ptype} prev", prev, rp, 1e-6)
+            ok &= report(f"ddim_step ptype={ptype} x0", x0, r0, 1e-6)
+        # time embedding
+        t = torch.tensor([999.0, 19.0, 500.0], device=dev)
+        out = torch.empty(3, 320, device=dev)
+        nat.timestep_sinusoid(t, 3, 320, True, 0.0, out)
+        half = 160
+        fr = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(half, device=dev) / half)
+        a = t[:, None] * fr[None]
+        ok &= report("timestep_sinusoid", out, torch.cat([a.cos(), a.sin()], -1), 1e-4)
+        x = torch.randn(3, 320, device=dev)
+        w = torch.randn(1280, 320, device=dev) / 18
+        b = torch.randn(1280, device=dev)
+        out = torch.empty(3, 1280, device=dev)
+        nat.small_linear(x, 3, 320, w, b, 1280, False, True, out, 1280)
+        ok &= report("small_linear silu_out", out, F.silu(x @ w.t() + b), 1e-5)
+        # convT shuffle + LN2d + SiLU
+        nb, h, w_, c = 1, 16, 16, 256
+        src = rnd(nb * h * w_, 4 * c)
+        g = torch.randn(c, device=dev)
+        be = torch.randn(c, device=dev)
+        out = torch.empty(nb * 4 * h * w_, c, device=dev, dtype=bf)
+        nat.convt_shuffle_ln(src, nb, h, w_, c, g, be, 1e-6, True, out)
+        s = src.float().reshape(nb, h, w_, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(nb, 2 * h, 2 * w_, c)
+        ref = F.silu(F.layer_norm(s, (c,), g, be, 1e-6)).reshape(-1, c)
+        ok &= report("convt_shuffle_ln", out, ref, 1e-2)
+        # bilinear x2
+        nb, h, w_, c = 2, 32, 64, 128
+        src = rnd(nb * h * w_, c)
+        out = torch.empty(nb, c, 2 * h, 2 * w_, device=dev)
+        nat.bilinear2x_to_nchw(src, nb, h, w_, c, c, out)
+        xi = src.float().reshape(nb, h, w_, c).permute(0, 3, 1, 2)
+        ref = F.interpolate(xi, scale_factor=2, mode="bilinear", align_corners=False)
+        ok &= report("bilinear2x_to_nchw", out, ref, 1e-5)
+        ids = torch.empty(nb, 2 * h, 2 * w_, device=dev, dtype=torch.uint8)
+        mp = torch.empty(nb, 2 * h, 2 * w_, device=dev)
+        nat.bilinear2x_argmax(src, nb, h, w_, c, c, ids, mp)
+        agree = (ids.long() == ref.argmax(1)).float().mean().item()
+        print(f"{'PASS' if agree > 0.999 else 'FAIL'} bilinear2x_argmax agreement={agree:.5f}")
+        ok &= agree > 0.999
+        ok &= report("bilinear2x_argmax maxprob", mp, ref.softmax(1).max(1)[0], 1e-4)
+    torch.cuda.synchronize()
+    print(f"GROUP {group}: {'OK' if ok else 'FAILED'}", flush=True)
+    return ok
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--group", default=None)
+    ap.add_argument("--timeout", type=int, default=240)
+    args = ap.parse_args()
+    if args.group:
+        sys.exit(0 if run_group(args.group) else 1)
+    bad = []
+    for g in GROUPS:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", g],
+                               timeout=args.timeout)
+            rc = r.returncode
+        except subprocess.TimeoutExpired:
+            rc = -999
+            print(f"GROUP {g}: TIMEOUT", flush=True)
+        print(f"--- group {g} rc={rc} ({time.time() - t0:.1f}s)", flush=True)
+        if rc != 0:
+            bad.append(g)
+    print("FAILED GROUPS:", bad if bad else "none")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
