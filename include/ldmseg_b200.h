@@ -104,6 +104,10 @@ int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int c1, int nb,
 int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma, const float* beta,
                      float eps, int silu, void* out, void* stream);
 
+/* Row softmax with scale (f32 scores -> bf16 probabilities): the fp32 softmax of diffusers 0.16.1
+ * AttentionBlock (single head, d = 512) in the AutoencoderKL mid block. */
+int ldmseg_softmax_rows(const float* s, int rows, int cols, float scale, void* out, void* stream);
+
 /* ---- attention -------------------------------------------------------------------------- *
  * softmax(Q K^T / sqrt(d)) V per (image, head); replaces F.scaled_dot_product_attention in
  * diffusers AttnProcessor2_0 (self-attention only; cross-attention is removed by
@@ -130,6 +134,9 @@ int ldmseg_nchw_to_nhwc_bf16(const float* src, int nb, int c, int hw, int cpad, 
 /* channel-last f32 [nb*hw, ld] (first c columns) -> NCHW f32, optional scale. */
 int ldmseg_nhwc_f32_to_nchw(const float* src, int nb, int c, int hw, int ld, float scale,
                             float* out, void* stream);
+/* NCHW f32 -> channel-last f32 [nb*hw, ld] (first c columns), optional scale. */
+int ldmseg_nchw_f32_to_nhwc(const float* src, int nb, int c, int hw, int ld, float scale, float* out,
+                            void* stream);
 /* channel-last bf16 [nb*hw, ld] -> NCHW f32 */
 int ldmseg_nhwc_bf16_to_nchw(const void* src, int nb, int c, int hw, int ld, float scale,
                              float* out, void* stream);
@@ -156,6 +163,14 @@ int ldmseg_sampler_step(const float* eps, float* latents, float* x0, const float
                         int nsteps, int self_cond, const float* mask, const float* known,
                         const float* noise, const float* sigma, void* stream);
 int ldmseg_advance_step(int* step_ptr, void* stream);
+/* Same update as ldmseg_ddim_step, but the timestep is a 0-dim int64 tensor ON THE DEVICE and the
+ * alphas_cumprod table (f32 [num_train_timesteps]) lives on the device too, so `step` needs no
+ * device->host synchronisation (the reference pays three per call: ddim_scheduler.py:234-235). */
+int ldmseg_ddim_step_indexed(const float* model_out, const float* sample, int64_t n,
+                             const int64_t* timestep_dev, const float* alphas_cumprod_dev,
+                             int step_ratio, float final_alpha, int prediction_type, int clip,
+                             float clip_range, int use_clipped, float* prev_sample, float* pred_x0,
+                             void* stream);
 
 /* ---- time embedding --------------------------------------------------------------------- *
  * y[r, :] = act_out( W x_act(r) + b ), f32, small-batch (r = timesteps): Timesteps sinusoid,
@@ -164,6 +179,10 @@ int ldmseg_timestep_sinusoid(const float* t, int rows, int dim, int flip_sin_to_
                              float freq_shift, float* out, void* stream);
 int ldmseg_small_linear(const float* x, int rows, int k, const float* w, const float* b, int n,
                         int silu_in, int silu_out, float* out, int out_ld, void* stream);
+/* dst[b, :] = table[*step_ptr, :] for b < nb: selects the current step's precomputed time-embedding
+ * biases inside a captured graph (the step index lives in device memory). */
+int ldmseg_select_row(const float* table, int ncols, const int* step_ptr, int nb, float* dst,
+                      void* stream);
 
 /* ---- seg decoder tail ------------------------------------------------------------------- *
  * ConvTranspose2d(k2,s2) output comes out of ldmseg_igemm as [M, 4*c] (tap-major columns);

@@ -104,6 +104,17 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int nb, int c
           __float2bfloat16(__ldg(src + (b * c + ch) * hw + p) * scale + shift);
   }
 }
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, int nb, int c, int hw, int ld,
+                                        float scale, float* __restrict__ out) {
+  const long long total = static_cast<long long>(nb) * hw * c;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const long long pix = i / c;
+    const long long b = pix / hw, p = pix - b * hw;
+    out[pix * ld + ch] = __ldg(src + (b * c + ch) * hw + p) * scale;
+  }
+}
 __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int nb, int c, int hw, int ld,
                                         float scale, float* __restrict__ out) {
   const long long total = static_cast<long long>(nb) * c * hw;
@@ -243,28 +254,72 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int rows, int dim, 
     o[half + k] = c;
   }
 }
-// y[r, j] = act_out(b[j] + sum_k w[j,k] * act_in(x[r,k])), one warp per (r, j)
+// y[r, j] = act_out(b[j] + sum_k w[j,k] * act_in(x[r,k])); one warp per output column j, looping
+// over rows in chunks of 8 so each weight row is streamed from HBM once.
 __global__ void small_linear_kernel(const float* __restrict__ x, int rows, int k,
                                     const float* __restrict__ w, const float* __restrict__ b, int n,
                                     int silu_in, int silu_out, float* __restrict__ out, int out_ld) {
-  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (wid >= static_cast<long long>(rows) * n) return;
-  const int r = static_cast<int>(wid / n), j = static_cast<int>(wid % n);
-  const float* xr = x + static_cast<size_t>(r) * k;
+  if (j >= n) return;
   const float* wr = w + static_cast<size_t>(j) * k;
-  float acc = 0.f;
-  for (int i = lane; i < k; i += 32) {
-    float xv = xr[i];
-    if (silu_in) xv = xv / (1.f + expf(-xv));
-    acc += xv * __ldg(wr + i);
-  }
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    float acc[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    acc += b ? b[j] : 0.f;
-    if (silu_out) acc = acc / (1.f + expf(-acc));
-    out[static_cast<size_t>(r) * out_ld + j] = acc;
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int c = lane; c < k; c += 32) {
+      const float wv = __ldg(wr + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r0 + i < rows) {
+          float xv = x[static_cast<size_t>(r0 + i) * k + c];
+          if (silu_in) xv = xv / (1.f + expf(-xv));
+          acc[i] += xv * wv;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && r0 + i < rows) {
+        a += b ? b[j] : 0.f;
+        if (silu_out) a = a / (1.f + expf(-a));
+        out[static_cast<size_t>(r0 + i) * out_ld + j] = a;
+      }
+    }
+  }
+}
+
+// dst[b, :] = table[*step_ptr, :] for every image b (per-step time-embedding bias selection)
+__global__ void select_row_kernel(const float* __restrict__ table, int ncols,
+                                  const int* __restrict__ step_ptr, int nb, float* __restrict__ dst) {
+  const int step = *step_ptr;
+  const long long total = static_cast<long long>(nb) * ncols;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = table[static_cast<size_t>(step) * ncols + (i % ncols)];
+}
+
+// DDIM step with the timestep read from device memory (no host synchronisation).
+__global__ void ddim_step_indexed_kernel(const float* __restrict__ mo, const float* __restrict__ x,
+                                         long long n, const long long* __restrict__ t_ptr,
+                                         const float* __restrict__ acp, int step_ratio,
+                                         float final_alpha, int ptype, int clip, float clip_range,
+                                         int use_clipped, float* __restrict__ prev,
+                                         float* __restrict__ x0o) {
+  const long long t = *t_ptr;
+  const long long tp = t - step_ratio;
+  const float a_t = acp[t];
+  const float a_p = tp >= 0 ? acp[tp] : final_alpha;
+  const float sa_t = sqrtf(a_t), sb_t = sqrtf(1.f - a_t), sa_p = sqrtf(a_p), sb_p = sqrtf(1.f - a_p);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float pv, x0;
+    ddim_update(mo[i], x[i], sa_t, sb_t, sa_p, sb_p, ptype, clip, clip_range, use_clipped, pv, x0);
+    if (prev) prev[i] = pv;
+    if (x0o) x0o[i] = x0;
   }
 }
 
@@ -403,6 +458,14 @@ extern "C" int ldmseg_nhwc_f32_to_nchw(const float* src, int nb, int c, int hw, 
   return check_launch("nhwc_f32_to_nchw_kernel");
 }
 
+extern "C" int ldmseg_nchw_f32_to_nhwc(const float* src, int nb, int c, int hw, int ld, float scale,
+                                       float* out, void* stream) {
+  LDM_REQUIRE(src && out && ld >= c, "nchw_f32_to_nhwc: bad arguments");
+  const long long total = static_cast<long long>(nb) * c * hw;
+  nchw_f32_to_nhwc_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(src, nb, c, hw, ld, scale, out);
+  return check_launch("nchw_f32_to_nhwc_kernel");
+}
+
 extern "C" int ldmseg_nhwc_bf16_to_nchw(const void* src, int nb, int c, int hw, int ld, float scale,
                                         float* out, void* stream) {
   LDM_REQUIRE(src && out, "nhwc_bf16_to_nchw: null pointer");
@@ -463,11 +526,32 @@ extern "C" int ldmseg_small_linear(const float* x, int rows, int k, const float*
                                    int n, int silu_in, int silu_out, float* out, int out_ld,
                                    void* stream) {
   LDM_REQUIRE(x && w && out, "small_linear: null pointer");
-  const long long warps = static_cast<long long>(rows) * n;
-  const int wpb = 8;
-  small_linear_kernel<<<static_cast<unsigned>((warps + wpb - 1) / wpb), wpb * 32, 0, ST(stream)>>>(
-      x, rows, k, w, b, n, silu_in, silu_out, out, out_ld);
+  const int wpb = 4;
+  small_linear_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, ST(stream)>>>(x, rows, k, w, b, n, silu_in,
+                                                                        silu_out, out, out_ld);
   return check_launch("small_linear_kernel");
+}
+
+extern "C" int ldmseg_select_row(const float* table, int ncols, const int* step_ptr, int nb,
+                                 float* dst, void* stream) {
+  LDM_REQUIRE(table && step_ptr && dst, "select_row: null pointer");
+  const long long total = static_cast<long long>(nb) * ncols;
+  select_row_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(table, ncols, step_ptr, nb, dst);
+  return check_launch("select_row_kernel");
+}
+
+extern "C" int ldmseg_ddim_step_indexed(const float* model_out, const float* sample, int64_t n,
+                                        const int64_t* timestep_dev, const float* alphas_cumprod_dev,
+                                        int step_ratio, float final_alpha, int prediction_type,
+                                        int clip, float clip_range, int use_clipped,
+                                        float* prev_sample, float* pred_x0, void* stream) {
+  LDM_REQUIRE(model_out && sample && timestep_dev && alphas_cumprod_dev, "ddim_step_indexed: null pointer");
+  LDM_REQUIRE(prediction_type >= 0 && prediction_type <= 2, "ddim_step_indexed: bad prediction_type");
+  if (n == 0) return 0;
+  ddim_step_indexed_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+      model_out, sample, n, reinterpret_cast<const long long*>(timestep_dev), alphas_cumprod_dev,
+      step_ratio, final_alpha, prediction_type, clip, clip_range, use_clipped, prev_sample, pred_x0);
+  return check_launch("ddim_step_indexed_kernel");
 }
 
 static int launch_bilinear(bool argmax, const void* src, int src_is_f32, int nb, int h, int w, int c,

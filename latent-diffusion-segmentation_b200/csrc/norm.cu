@@ -263,9 +263,60 @@ __global__ void convt_shuffle_ln_kernel(const __nv_bfloat16* __restrict__ src, i
   }
 }
 
+// ---- row softmax: out[r, :] = softmax(scale * s[r, :]) (f32 in, bf16 out), one CTA per row ------
+// Used by the single-head (d = 512) spatial attention of the AutoencoderKL mid block
+// (diffusers 0.16.1 AttentionBlock: softmax in fp32 over baddbmm scores).
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int cols, float scale,
+                                    __nv_bfloat16* __restrict__ out) {
+  __shared__ float red[32];
+  const float* row = s + static_cast<size_t>(blockIdx.x) * cols;
+  __nv_bfloat16* orow = out + static_cast<size_t>(blockIdx.x) * cols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    sum += __expf((v.x - mx) * scale) + __expf((v.y - mx) * scale) + __expf((v.z - mx) * scale) +
+           __expf((v.w - mx) * scale);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    uint2 u;
+    u.x = pack_bf16x2(__expf((v.x - mx) * scale) * inv, __expf((v.y - mx) * scale) * inv);
+    u.y = pack_bf16x2(__expf((v.z - mx) * scale) * inv, __expf((v.w - mx) * scale) * inv);
+    *reinterpret_cast<uint2*>(orow + i) = u;
+  }
+}
+
 }  // namespace ldm
 
 using namespace ldm;
+
+extern "C" int ldmseg_softmax_rows(const float* s, int rows, int cols, float scale, void* out,
+                                   void* stream) {
+  LDM_REQUIRE(s && out && cols % 4 == 0, "softmax_rows: bad arguments");
+  softmax_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s, cols, scale, reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("softmax_rows_kernel");
+}
 
 extern "C" int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int c1, int nb, int hw,
                                 int groups, const float* gamma, const float* beta, float eps,

@@ -27,7 +27,7 @@ EXPORTS = [
     "ldmseg_nchw_to_nhwc_bf16", "ldmseg_nhwc_f32_to_nchw", "ldmseg_nhwc_bf16_to_nchw",
     "ldmseg_ddim_step", "ldmseg_sampler_step", "ldmseg_advance_step", "ldmseg_timestep_sinusoid",
     "ldmseg_small_linear", "ldmseg_convt_shuffle_ln", "ldmseg_bilinear2x_to_nchw",
-    "ldmseg_bilinear2x_argmax",
+    "ldmseg_bilinear2x_argmax", "ldmseg_select_row", "ldmseg_ddim_step_indexed", "ldmseg_softmax_rows", "ldmseg_nchw_f32_to_nhwc",
 ]
 
 
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         "ldmseg_nchw_to_nhwc_bf16": [vp, i32, i32, i32, i32, i32, f32, f32, vp, vp],
         "ldmseg_nhwc_f32_to_nchw": [vp, i32, i32, i32, i32, f32, vp, vp],
         "ldmseg_nhwc_bf16_to_nchw": [vp, i32, i32, i32, i32, f32, vp, vp],
+        "ldmseg_nchw_f32_to_nhwc": [vp, i32, i32, i32, i32, f32, vp, vp],
         "ldmseg_ddim_step": [vp, vp, i64, f32, f32, i32, i32, f32, i32, f32, vp, vp, vp, vp],
         "ldmseg_sampler_step": [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp],
         "ldmseg_advance_step": [vp, vp],
@@ -101,6 +102,9 @@ def load() -> C.CDLL:
         "ldmseg_convt_shuffle_ln": [vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp],
         "ldmseg_bilinear2x_to_nchw": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
         "ldmseg_bilinear2x_argmax": [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+        "ldmseg_select_row": [vp, i32, vp, i32, vp, vp],
+        "ldmseg_softmax_rows": [vp, i32, i32, f32, vp, vp],
+        "ldmseg_ddim_step_indexed": [vp, vp, i64, vp, vp, i32, f32, i32, i32, f32, i32, vp, vp, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -271,3 +275,26 @@ def bilinear2x_argmax(src, nb, h, w, c, ld, ids, maxprob=None) -> None:
     _check(load().ldmseg_bilinear2x_argmax(_ptr(src), int(src.dtype == torch.float32), nb, h, w, c,
                                            ld, _ptr(ids), _ptr(maxprob), _stream()),
            "ldmseg_bilinear2x_argmax")
+
+
+def select_row(table, ncols, step_ptr, nb, dst) -> None:
+    _check(load().ldmseg_select_row(_ptr(table), ncols, _ptr(step_ptr), nb, _ptr(dst), _stream()),
+           "ldmseg_select_row")
+
+
+def ddim_step_indexed(model_out, sample, timestep_dev, acp_dev, step_ratio, final_alpha, ptype, clip,
+                      clip_range, use_clipped, prev, x0) -> None:
+    _check(load().ldmseg_ddim_step_indexed(_ptr(model_out), _ptr(sample), model_out.numel(),
+                                           _ptr(timestep_dev), _ptr(acp_dev), step_ratio, final_alpha,
+                                           ptype, int(clip), clip_range, int(use_clipped), _ptr(prev),
+                                           _ptr(x0), _stream()), "ldmseg_ddim_step_indexed")
+
+
+def softmax_rows(s, rows, cols, scale, out) -> None:
+    _check(load().ldmseg_softmax_rows(_ptr(s), rows, cols, scale, _ptr(out), _stream()),
+           "ldmseg_softmax_rows")
+
+
+def nchw_f32_to_nhwc(src, nb, c, hw, ld, scale, out) -> None:
+    _check(load().ldmseg_nchw_f32_to_nhwc(_ptr(src), nb, c, hw, ld, scale, _ptr(out), _stream()),
+           "ldmseg_nchw_f32_to_nhwc")

@@ -25,6 +25,14 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(n, 9 * cp)
 
 
+def pack_conv3x3_im2col(w: torch.Tensor) -> torch.Tensor:
+    """[N, C, 3, 3] -> [N, pad64(9*C)] for convs fed by the im2col kernel (taps contiguous, no per-tap
+    padding; identical to pack_conv3x3 when C is a multiple of 64)."""
+    n, c, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    return pack_linear(w.float().permute(0, 2, 3, 1).reshape(n, 9 * c))
+
+
 def pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[N, K] (or [N, K, 1, 1]) -> [N, pad64(K)]."""
     if w.dim() == 4:

@@ -1,0 +1,276 @@
+"""Executes the conditional UNet forward on the hand-written sm_100a kernels.
+
+Replaces the diffusers-0.16.1 block forwards that /root/reference/ldmseg/models/unet.py:281-436
+drives (conv_in -> 4 down blocks -> mid -> 4 up blocks -> GroupNorm/SiLU/conv_out).  The engine
+
+  * packs every weight once into the bf16 [N, K] layout of the tcgen05 implicit-GEMM kernel
+    (QKV fused to one N=3C GEMM, GEGLU rows interleaved for the fused epilogue, the resnet 1x1
+    shortcut appended as extra K segments of conv2, conv2+shortcut biases summed);
+  * keeps activations channel-last bf16 [pixels, C]; `torch.cat([hidden, skip])` of the up blocks is
+    never materialised un-normalised: GroupNorm reads both sources, the shortcut GEMM reads both;
+  * builds, per (batch, latent size), a static list of kernel launches over preallocated buffers
+    (a "plan") which the caller may capture in a CUDA graph.
+
+Per forward at a 64x64 latent: 52 conv3x3 + 32 conv1x1 + 64 linear as igemm launches (the 14 1x1
+shortcuts ride inside conv2), 16 attention launches, 61 GroupNorm, 32 LayerNorm.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from ldmseg import _native as nat
+from ldmseg import _pack as pk
+from .plan import PlanBase, WeightsBase
+
+
+class UNetWeights(WeightsBase):
+    """bf16-packed weights of a ldmseg.models.UNet, resident on the device."""
+
+    def __init__(self, unet, device):
+        super().__init__(device)
+        cfg = unet.config
+        self.block_out_channels = tuple(cfg.block_out_channels)
+        self.in_channels = unet.conv_in.in_channels
+        self.out_channels = unet.conv_out.out_channels
+        self.groups = cfg.norm_num_groups
+        self.heads = cfg.attention_head_dim
+        self.cin_pad = (self.in_channels + 15) // 16 * 16
+        self._pack(unet)
+
+    def _transformer(self, name, t):
+        c = t.channels
+        self._norm(name + ".norm", t.norm)
+        self._gemm(name + ".proj_in", pk.pack_linear(t.proj_in.weight), t.proj_in.bias, c)
+        blk = t.transformer_blocks[0]
+        if blk.attn2 is not None:
+            raise NotImplementedError(
+                "ldmseg_b200 UNet engine: cross-attention is not built (LDMSeg's released configuration "
+                "removes it: image_descriptors='remove', ldmseg/models/descriptors.py:94-96). Call "
+                "unet.remove_cross_attention() first.")
+        self._norm(name + ".ln1", blk.norm1)
+        self._norm(name + ".ln3", blk.norm3)
+        a = blk.attn1
+        wqkv = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], dim=0)
+        self._gemm(name + ".qkv", pk.pack_linear(wqkv), None, 3 * c)
+        self._gemm(name + ".to_out", pk.pack_linear(a.to_out[0].weight), a.to_out[0].bias, c)
+        wi, bi = pk.interleave_geglu(blk.ff.net[0].proj.weight.detach().float(),
+                                     blk.ff.net[0].proj.bias.detach().float())
+        self._gemm(name + ".ff1", pk.pack_linear(wi), bi, wi.shape[0])
+        self._gemm(name + ".ff2", pk.pack_linear(blk.ff.net[2].weight), blk.ff.net[2].bias, c)
+        self._gemm(name + ".proj_out", pk.pack_linear(t.proj_out.weight), t.proj_out.bias, c)
+
+    def _pack(self, unet):
+        boc = self.block_out_channels
+        # time embedding stays fp32 (tiny; evaluated once per forward or precomputed for all steps)
+        te = unet.time_embedding
+        self.time_proj = (unet.time_proj.num_channels, bool(unet.time_proj.flip_sin_to_cos),
+                          float(unet.time_proj.downscale_freq_shift))
+        self.te_w1, self.te_b1 = self._dev(te.linear_1.weight.float()), self._dev(te.linear_1.bias.float())
+        self.te_w2, self.te_b2 = self._dev(te.linear_2.weight.float()), self._dev(te.linear_2.bias.float())
+        self.temb_dim = te.linear_2.out_features
+        tproj_w, tproj_b, self.temb_off = [], [], {}
+        off = 0
+
+        def reg_temb(name, r):
+            nonlocal off
+            tproj_w.append(r.time_emb_proj.weight.detach().float())
+            tproj_b.append(r.time_emb_proj.bias.detach().float())
+            self.temb_off[name] = off
+            off += r.out_channels
+
+        # conv_in: input channels padded to a multiple of 16 (TMA rows of >= 32 bytes)
+        w = unet.conv_in.weight.detach().float()
+        wp = torch.zeros(w.shape[0], self.cin_pad, 3, 3, device=w.device)
+        wp[:, : w.shape[1]] = w
+        self._gemm("conv_in", pk.pack_conv3x3(wp), unet.conv_in.bias, boc[0])
+
+        for i, blk in enumerate(unet.down_blocks):
+            for j, r in enumerate(blk.resnets):
+                nm = f"down{i}.res{j}"
+                self._resnet(nm, r, [r.in_channels])
+                reg_temb(nm, r)
+                if hasattr(blk, "attentions"):
+                    self._transformer(f"down{i}.attn{j}", blk.attentions[j])
+            if blk.downsamplers is not None:
+                d = blk.downsamplers[0].conv
+                self._gemm(f"down{i}.down", pk.pack_conv3x3_im2col(d.weight), d.bias, d.out_channels)
+        for j, r in enumerate(unet.mid_block.resnets):
+            self._resnet(f"mid.res{j}", r, [r.in_channels])
+            reg_temb(f"mid.res{j}", r)
+        self._transformer("mid.attn0", unet.mid_block.attentions[0])
+        # skip channel bookkeeping: order of down_block_res_samples (unet.py:360-373)
+        skips = [boc[0]]
+        for i, blk in enumerate(unet.down_blocks):
+            skips += [boc[i]] * len(blk.resnets)
+            if blk.downsamplers is not None:
+                skips.append(boc[i])
+        for i, blk in enumerate(unet.up_blocks):
+            for j, r in enumerate(blk.resnets):
+                cskip = skips.pop()
+                chid = r.in_channels - cskip
+                nm = f"up{i}.res{j}"
+                self._resnet(nm, r, [chid, cskip])  # shortcut reads (hidden, skip) as two K segments
+                reg_temb(nm, r)
+                if hasattr(blk, "attentions"):
+                    self._transformer(f"up{i}.attn{j}", blk.attentions[j])
+            if blk.upsamplers is not None:
+                u = blk.upsamplers[0].conv
+                self._gemm(f"up{i}.up", pk.pack_conv3x3(u.weight), u.bias, u.out_channels)
+        self._norm("norm_out", unet.conv_norm_out)
+        self._gemm("conv_out", pk.pack_conv3x3(unet.conv_out.weight), unet.conv_out.bias, self.out_channels)
+        self.tproj_w = self._dev(torch.cat(tproj_w, dim=0))
+        self.tproj_b = self._dev(torch.cat(tproj_b, dim=0))
+        self.temb_total = off
+        self.structure = [(hasattr(b, "attentions"), len(b.resnets), b.downsamplers is not None)
+                          for b in unet.down_blocks]
+        self.up_structure = [(hasattr(b, "attentions"), len(b.resnets), b.upsamplers is not None)
+                             for b in unet.up_blocks]
+
+    # ---- time embedding (fp32 CUDA kernels): Timesteps -> TimestepEmbedding -> 22 x time_emb_proj
+    def time_embedding(self, t_float: torch.Tensor, out: torch.Tensor) -> None:
+        """t_float f32 [rows] on device -> out f32 [rows, temb_total] (unet.py:303-307 + the
+        `time_emb_proj(SiLU(emb))` of every ResnetBlock2D)."""
+        rows = t_float.numel()
+        dim, flip, shift = self.time_proj
+        sin = torch.empty(rows, dim, device=self.device)
+        nat.timestep_sinusoid(t_float, rows, dim, flip, shift, sin)
+        h = torch.empty(rows, self.temb_dim, device=self.device)
+        nat.small_linear(sin, rows, dim, self.te_w1, self.te_b1, self.temb_dim, False, True, h, self.temb_dim)
+        emb = torch.empty(rows, self.temb_dim, device=self.device)
+        nat.small_linear(h, rows, self.temb_dim, self.te_w2, self.te_b2, self.temb_dim, False, False, emb,
+                         self.temb_dim)
+        nat.small_linear(emb, rows, self.temb_dim, self.tproj_w, self.tproj_b, self.temb_total, True, False,
+                         out, self.temb_total)
+
+
+class UNetPlan(PlanBase):
+    """Launch list of one UNet forward for a fixed (batch, latent size).
+
+    Inputs live in `x_in` (bf16 [M, cin_pad]) and `temb` (f32 [nb, temb_total]); the predicted noise
+    lands in `eps` (f32 [M, 4], channel-last)."""
+
+    def __init__(self, W: UNetWeights, nb: int, size: int):
+        super().__init__(W, nb)
+        self.size = size
+        m0 = nb * size * size
+        self.x_in = torch.zeros(m0, W.cin_pad, device=self.device, dtype=torch.bfloat16)
+        self.temb = torch.zeros(nb, W.temb_total, device=self.device, dtype=torch.float32)
+        self.eps = torch.zeros(m0, 4, device=self.device, dtype=torch.float32)
+        self.rowbias_ld = W.temb_total
+        self._build()
+
+    def _res(self, name, x, cx, skip, cskip, h):
+        return self._resnet(name, x, cx, skip, cskip, h, rowbias=self.temb[:, self.W.temb_off[name]:])
+
+    def _transformer(self, name, x, c, h):
+        W, nb = self.W, self.nb
+        hw, m = h * h, self.nb * h * h
+        heads = W.heads
+        d = c // heads
+        g = self._buf(m, c)
+        self._gn(name + ".norm", x, c, None, 0, hw, False, g)
+        t0 = self._buf(m, c)
+        self._gemm(W.L[name + ".proj_in"], [g], [c], 1, 1, m, [(0, 1)], t0)
+        ln = self._buf(m, c)
+        self._ln(name + ".ln1", t0, m, c, ln)
+        qkv = self._buf(m, 3 * c)
+        self._gemm(W.L[name + ".qkv"], [ln], [c], 1, 1, m, [(0, 1)], qkv)
+        ao = self._buf(m, c)
+        self._op(lambda: nat.attention(qkv, nb, hw, heads, d, ao))
+        t1 = self._buf(m, c)
+        self._gemm(W.L[name + ".to_out"], [ao], [c], 1, 1, m, [(0, 1)], t1, residual=t0)
+        ln2 = self._buf(m, c)
+        self._ln(name + ".ln3", t1, m, c, ln2)
+        ff = self._buf(m, 4 * c)
+        self._gemm(W.L[name + ".ff1"], [ln2], [c], 1, 1, m, [(0, 1)], ff, act=nat.ACT_GEGLU)
+        t2 = self._buf(m, c)
+        self._gemm(W.L[name + ".ff2"], [ff], [4 * c], 1, 1, m, [(0, 1)], t2, residual=t1)
+        out = self._buf(m, c)
+        self._gemm(W.L[name + ".proj_out"], [t2], [c], 1, 1, m, [(0, 1)], out, residual=x)
+        return out
+
+    def _build(self):
+        W, nb = self.W, self.nb
+        boc = W.block_out_channels
+        h = self.size
+        x = self._buf(nb * h * h, boc[0])
+        self._gemm(W.L["conv_in"], [self.x_in], [W.cin_pad], nb, h, h, [(0, 9)], x)
+        c = boc[0]
+        skips = [(x, c, h)]
+        for i, (has_attn, nres, has_down) in enumerate(W.structure):
+            for j in range(nres):
+                x = self._res(f"down{i}.res{j}", x, c, None, 0, h)
+                c = boc[i]
+                if has_attn:
+                    x = self._transformer(f"down{i}.attn{j}", x, c, h)
+                skips.append((x, c, h))
+            if has_down:
+                col = self._buf(nb * (h // 2) * (h // 2), 9 * c)
+                self._op(lambda x=x, h=h, c=c, col=col: nat.im2col_s2(x, nb, h, h, c, 1, col))
+                h //= 2
+                y = self._buf(nb * h * h, c)
+                self._gemm(W.L[f"down{i}.down"], [col], [9 * c], 1, 1, nb * h * h, [(0, 1)], y)
+                x = y
+                skips.append((x, c, h))
+        x = self._res("mid.res0", x, c, None, 0, h)
+        x = self._transformer("mid.attn0", x, c, h)
+        x = self._res("mid.res1", x, c, None, 0, h)
+        for i, (has_attn, nres, has_up) in enumerate(W.up_structure):
+            for j in range(nres):
+                s, cs, hs = skips.pop()
+                assert hs == h, (hs, h)
+                x = self._res(f"up{i}.res{j}", x, c, s, cs, h)
+                c = W.L[f"up{i}.res{j}.conv1"].n
+                if has_attn:
+                    x = self._transformer(f"up{i}.attn{j}", x, c, h)
+            if has_up:
+                up = self._buf(nb * 4 * h * h, c)
+                self._op(lambda x=x, h=h, c=c, up=up: nat.upsample2x(x, nb, h, h, c, up))
+                h *= 2
+                y = self._buf(nb * h * h, c)
+                self._gemm(W.L[f"up{i}.up"], [up], [c], nb, h, h, [(0, 9)], y)
+                x = y
+        a = self._buf(nb * h * h, c)
+        self._gn("norm_out", x, c, None, 0, h * h, True, a)
+        self._gemm(W.L["conv_out"], [a], [c], nb, h, h, [(0, 9)], self.eps)
+
+
+class UNetEngine:
+    def __init__(self, unet):
+        dev = next(unet.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("ldmseg_b200: UNet must live on a CUDA device (no CPU fallback); call .to('cuda')")
+        nat.load()
+        with torch.cuda.device(dev):
+            self.weights = UNetWeights(unet, dev)
+        self.device = dev
+        self.plans: Dict[Tuple[int, int], UNetPlan] = {}
+
+    def plan(self, nb: int, size: int) -> UNetPlan:
+        key = (nb, size)
+        if key not in self.plans:
+            with torch.cuda.device(self.device):
+                self.plans[key] = UNetPlan(self.weights, nb, size)
+        return self.plans[key]
+
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        """sample f32 NCHW [B, C, L, L] (C = conv_in channels), timesteps [B] -> eps f32 NCHW [B, 4, L, L]."""
+        nb, c, hgt, wid = sample.shape
+        if hgt != wid:
+            raise RuntimeError("ldmseg_b200: square latents only (as the reference's sample(), "
+                               "trainers_ldm_cond.py:1089)")
+        if c != self.weights.in_channels:
+            raise RuntimeError(f"UNet expects {self.weights.in_channels} input channels, got {c}")
+        plan = self.plan(nb, hgt)
+        with torch.cuda.device(self.device):
+            tf = timesteps.to(device=self.device, dtype=torch.float32).contiguous()
+            self.weights.time_embedding(tf, plan.temb)
+            nat.nchw_to_nhwc_bf16(sample.contiguous(), nb, c, hgt * wid, self.weights.cin_pad, 0, 1.0, 0.0,
+                                  plan.x_in)
+            plan.run()
+            out = torch.empty(nb, 4, hgt, wid, device=self.device, dtype=torch.float32)
+            nat.nhwc_f32_to_nchw(plan.eps, nb, 4, hgt * wid, 4, 1.0, out)
+        return out
