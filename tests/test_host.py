@@ -1,0 +1,136 @@
+"""CPU tests of the host logic and of the C-ABI boundary (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(_built_library):
+    hdr = open(os.path.join(ROOT, "include", "ldmseg_b200.h")).read()
+    declared = set(re.findall(r"\b(ldmseg_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("ldmseg_igemm_params")
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_built_library)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ldmseg_b200.h but not exported"
+    from ldmseg import _native as nat
+    assert set(nat.EXPORTS) == declared
+    assert nat.load().ldmseg_version() == 1
+
+
+def test_igemm_params_struct_layout_matches_header():
+    """ctypes mirror of ldmseg_igemm_params: field order / count as in the header."""
+    from ldmseg import _native as nat
+    hdr = open(os.path.join(ROOT, "include", "ldmseg_b200.h")).read()
+    body = hdr[hdr.index("typedef struct ldmseg_igemm_params {"):hdr.index("} ldmseg_igemm_params;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"([a-z_]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
+    fields = [f[0] for f in nat.IgemmParams._fields_]
+    assert fields == names and len(fields) == 25
+
+
+def test_product_scheduler_host_logic_matches_reference(golden_dir):
+    from ldmseg.schedulers import DDIMNoiseScheduler
+    from oracle.make_golden import SCHED_KW
+    g = np.load(f"{golden_dir}/scheduler.npz")
+    s = DDIMNoiseScheduler(**SCHED_KW)
+    np.testing.assert_array_equal(s.alphas_cumprod.numpy(), g["alphas_cumprod"])
+    np.testing.assert_array_equal(s.final_alpha_cumprod.numpy(), g["final_alpha_cumprod"])
+    for n in (10, 50, 100):
+        s.set_timesteps_inference(n)
+        np.testing.assert_array_equal(s.timesteps.numpy(), g[f"timesteps_{n}"])
+        assert s.steps_offset == 1000 // n - 1          # Q3: the config value is overwritten
+    for name in ("linear", "squaredcos_cap_v2", "sigmoid"):
+        np.testing.assert_array_equal(DDIMNoiseScheduler(**dict(SCHED_KW, beta_schedule=name)).alphas_cumprod.numpy(),
+                                      g[f"alphas_cumprod_{name}"])
+    eps, x = torch.from_numpy(g["eps"]), torch.from_numpy(g["x"])
+    t = torch.tensor([999, 19])
+    noisy = s.add_noise(x, eps.clone(), t)
+    np.testing.assert_array_equal(noisy.numpy(), g["add_noise"])
+    np.testing.assert_array_equal(s.remove_noise(noisy, eps, t).numpy(), g["remove_noise"])
+    assert len(s) == 1000 and s.init_noise_sigma == 1.0 and "DDIMScheduler(" in str(s)
+    with pytest.raises(NotImplementedError):
+        DDIMNoiseScheduler(beta_schedule="nope")
+    with pytest.raises(RuntimeError):                    # the hot call has no CPU fallback
+        s.step(eps, s.timesteps[0], x)
+
+
+def test_product_state_dict_keys_match_reference(golden_dir):
+    from ldmseg.models import UNet, GeneralVAESeg
+    from oracle.make_golden import TINY, VAE_KW
+    g = np.load(f"{golden_dir}/unet_glue_tiny.npz")
+    unet = UNet(**TINY)
+    unet.remove_cross_attention()
+    unet.modify_encoder(in_channels=8, init_mode_seg="copy", init_mode_image="zero", cond_channels=4)
+    assert sorted(unet.state_dict().keys()) == list(g["state_keys"])
+    assert sum(p.numel() for p in unet.parameters()) == int(g["n_params"])
+    assert torch.all(unet.conv_in.weight[:, 4:] == 0) and unet.conv_in.weight.shape == (320, 12, 3, 3)
+    gs = np.load(f"{golden_dir}/segvae.npz")
+    vae = GeneralVAESeg(**VAE_KW)
+    assert sorted(vae.state_dict().keys()) == list(gs["state_keys"])
+    assert vae.downsample_factor == 8 and vae.interpolation_factor == 2
+    with pytest.raises(RuntimeError):
+        unet(torch.zeros(1, 12, 16, 16), torch.tensor(1), None)
+    with pytest.raises(RuntimeError):
+        vae.decode(torch.zeros(1, 4, 8, 8))
+    with torch.device("meta"):
+        full = UNet()
+        full.remove_cross_attention()
+        full.modify_encoder(in_channels=8, cond_channels=4)
+    assert sum(p.numel() for p in full.parameters()) == 815_556_484
+
+
+def test_output_dict_and_descriptors():
+    from ldmseg.utils import OutputDict
+    from ldmseg.models import get_image_descriptor_model, UNet
+    from oracle.make_golden import TINY
+    o = OutputDict(sample=1)
+    o["x"] = 2
+    assert o.sample == 1 and o.x == 2 and list(o.keys()) == ["sample", "x"]
+    unet = UNet(**TINY)
+    assert get_image_descriptor_model("remove", None, unet) == (None, None, None)
+    assert all(tb.attn2 is None for b in unet.down_blocks if hasattr(b, "attentions")
+               for a in b.attentions for tb in a.transformer_blocks)
+    with pytest.raises(NotImplementedError):
+        get_image_descriptor_model("dino_image", None, unet)
+
+
+def test_weight_packing_is_a_valid_gemm_layout():
+    """pack_* layouts reproduce F.conv2d / F.linear when multiplied against an explicit im2col (host logic)."""
+    import torch.nn.functional as F
+    from ldmseg import _pack as pk
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(24, 40, 3, 3, generator=g)
+    x = torch.randn(2, 40, 8, 8, generator=g)
+    ref = F.conv2d(x, w, padding=1).permute(0, 2, 3, 1).reshape(-1, 24)
+    cols = F.unfold(x, 3, padding=1).reshape(2, 40, 9, 64).permute(0, 3, 2, 1)       # [n, pix, tap, c]
+    cols = F.pad(cols, (0, 24)).reshape(2 * 64, 9 * 64)                              # channels padded to 64
+    torch.testing.assert_close(cols @ pk.pack_conv3x3(w).t(), ref, rtol=1e-4, atol=1e-4)
+    cols2 = F.unfold(x, 3, padding=1).reshape(2, 40, 9, 64).permute(0, 3, 2, 1).reshape(128, 360)
+    torch.testing.assert_close(F.pad(cols2, (0, 24)) @ pk.pack_conv3x3_im2col(w).t(), ref, rtol=1e-4, atol=1e-4)
+    wl, bl = torch.randn(64, 16, generator=g), torch.randn(64, generator=g)
+    wi, bi = pk.interleave_geglu(wl, bl)
+    y = torch.randn(5, 16, generator=g) @ wi.t() + bi
+    h, gate = (torch.randn(5, 16, generator=torch.Generator().manual_seed(0)) * 0, None)
+    r = y.reshape(5, 2, 2, 16)
+    xin = torch.linalg.lstsq(wi, (y - bi).t()).solution.t()
+    full = xin @ wl.t() + bl
+    torch.testing.assert_close(r[:, :, 0].reshape(5, 32), full[:, :32], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(r[:, :, 1].reshape(5, 32), full[:, 32:], rtol=1e-3, atol=1e-3)
+    wt, bt = pk.pack_convT2x2(torch.randn(8, 6, 2, 2, generator=g), torch.randn(6, generator=g))
+    assert wt.shape == (24, 64) and bt.shape == (24,)
+
+
+def test_tiling_heuristic():
+    from ldmseg.engine.plan import choose_tiling
+    bn, split = choose_tiling(4096, 320, 45)
+    assert bn in (64, 128, 160, 256) and split >= 1
+    bn, split = choose_tiling(64, 1280, 360)          # 8x8 level at batch 1: weight streaming -> split-K
+    assert split > 1 and ((64 + 127) // 128) * ((1280 + bn - 1) // bn) * split <= 148
+    bn, split = choose_tiling(8 * 4096, 2560, 5)      # plenty of tiles: no split
+    assert split == 1
