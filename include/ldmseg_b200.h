@@ -79,10 +79,18 @@ typedef struct ldmseg_igemm_params {
   int out_dtype;                     /* LDMSEG_OUT_* */
   int act;                           /* LDMSEG_ACT_* */
   /* scheduling */
-  int block_n;                       /* 0 = choose; else 64 / 128 / 256 */
+  int block_n;                       /* 0 = choose; else 64 / 128 / 160 / 256 */
   int split_k;                       /* 0/1 = none; >1 needs workspace */
-  float* workspace;                  /* split-K partials: f32 [M_pad, n_pad] zero-initialised */
-  int* tile_counters;                /* split-K: int32 per output tile, zero-initialised */
+  float* workspace;                  /* split-K partial tiles, f32, tiles*split_k*128*block_n elements */
+  int* tile_counters;                /* split-K: int32 per output tile, zero-initialised (self-resetting) */
+  long long workspace_elems;         /* capacity of workspace in f32 elements */
+  float* stats;                      /* optional f32 [nb, n, 2]: += per-(image, channel) sum and sum of
+                                        squares of the stored (bf16-rounded) output -- GroupNorm statistics
+                                        fused into the producer; caller zeroes it; needs h*w % 32 == 0 */
+  int stats_hw;                      /* rows per image for `stats` (0 = h*w); lets a plain [M, K] GEMM
+                                        (nb=1, h=1, w=M) produce per-image statistics */
+  int pdl;                           /* 1: launch with programmatic dependent launch (overlap the prologue
+                                        with the previous kernel's tail) */
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);
@@ -99,6 +107,15 @@ int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream);
 int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int c1, int nb, int hw, int groups,
                      const float* gamma, const float* beta, float eps, int silu, void* out,
                      float* stats, void* stream);
+/* Apply pass only: statistics come from the producers' fused per-(image, channel) {sum, sumsq}
+ * (ldmseg_igemm_params.stats), f32 [nb, c, 2] per source.  One launch per GroupNorm. */
+int ldmseg_groupnorm_apply_cs(const void* src0, int c0, const float* chan_stats0, const void* src1,
+                              int c1, const float* chan_stats1, int nb, int hw, int groups,
+                              const float* gamma, const float* beta, float eps, int silu, void* out,
+                              void* stream);
+/* Launch every kernel of the library with programmatic dependent launch (prologue of kernel i+1
+ * overlaps the tail of kernel i); returns the previous setting. */
+int ldmseg_set_pdl(int enable);
 /* LayerNorm over the channel dim of each row (tokens or pixels); replaces nn.LayerNorm in
  * BasicTransformerBlock.norm1/norm3 and LayerNorm2d (ldmseg/models/vae.py:309-322). */
 int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma, const float* beta,

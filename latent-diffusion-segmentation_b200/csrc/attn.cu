@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();  // the prologue above overlapped the previous kernel; inputs are read from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 template <int D>
 __global__ void attn_simple_kernel(const __nv_bfloat16* __restrict__ qkv, int nb, int ntok, int heads,
                                    __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   constexpr int TK = 32;
   __shared__ float sk[TK][D];
   __shared__ float sv[TK][D];
@@ -356,7 +358,7 @@ static int launch_attn(const void* qkv, int nb, int ntok, int heads, void* out, 
     configured = true;
   }
   const int grid = nb * heads * ((ntok + 127) / 128);
-  attn_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(kp);
+  launch_kernel(attn_kernel<D>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
   return check_launch("attn_kernel");
 }
 
@@ -386,9 +388,9 @@ extern "C" int ldmseg_attention_simple(const void* qkv, int nb, int ntok, int he
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   switch (d) {
-    case 40: attn_simple_kernel<40><<<grid, threads, 0, st>>>(q, nb, ntok, heads, o); break;
-    case 80: attn_simple_kernel<80><<<grid, threads, 0, st>>>(q, nb, ntok, heads, o); break;
-    case 160: attn_simple_kernel<160><<<grid, threads, 0, st>>>(q, nb, ntok, heads, o); break;
+    case 40: launch_kernel(attn_simple_kernel<40>, dim3(grid), dim3(threads), 0, st, q, nb, ntok, heads, o); break;
+    case 80: launch_kernel(attn_simple_kernel<80>, dim3(grid), dim3(threads), 0, st, q, nb, ntok, heads, o); break;
+    case 160: launch_kernel(attn_simple_kernel<160>, dim3(grid), dim3(threads), 0, st, q, nb, ntok, heads, o); break;
     default: set_error("attention_simple: unsupported head dim %d", d); return -2;
   }
   return check_launch("attn_simple_kernel");

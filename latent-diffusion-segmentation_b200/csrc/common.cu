@@ -10,6 +10,7 @@ namespace ldm {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launch_count{0};
+int g_pdl = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -75,4 +76,9 @@ extern "C" int ldmseg_version(void) { return LDMSEG_ABI_VERSION; }
 extern "C" const char* ldmseg_last_error_string(void) { return ldm::g_err; }
 extern "C" int64_t ldmseg_launch_count(void) {
   return ldm::g_launch_count.load(std::memory_order_relaxed);
+}
+extern "C" int ldmseg_set_pdl(int enable) {
+  const int old = ldm::g_pdl;
+  ldm::g_pdl = enable ? 1 : 0;
+  return old;
 }

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 namespace ldm {
 
@@ -41,6 +42,28 @@ inline int check_launch(const char* what) {
       return static_cast<int>(e__);                                           \
     }                                                                         \
   } while (0)
+
+// Programmatic dependent launch (PDL): when enabled (ldmseg_set_pdl), every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that its prologue overlaps the tail of the
+// previous kernel on the stream; all kernels execute `griddepcontrol.wait` before touching memory.
+extern int g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Encode a tiled, 128B-swizzled bf16 tensor map of the given rank (dims innermost first).
 // strides_bytes has rank-1 entries (stride of dims 1..rank-1).  Returns 0 on success.

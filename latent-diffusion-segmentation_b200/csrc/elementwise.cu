@@ -32,6 +32,7 @@ __device__ __forceinline__ uint4 pack8e(const float (&f)[8]) {
 // ---- GEGLU ------------------------------------------------------------------------------
 __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c,
                              __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const int c8 = c >> 3;
   const long long total = rows * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -52,6 +53,7 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, long long rows
 // ---- nearest x2 upsample ------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, int nb, int h, int w, int c8,
                                   uint4* __restrict__ out) {
+  pdl_sync();
   const long long total = static_cast<long long>(nb) * 4 * h * w * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -68,6 +70,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, int nb, int h, 
 // ---- im2col for 3x3 stride-2 -----------------------------------------------------------------
 __global__ void im2col_s2_kernel(const uint4* __restrict__ src, int nb, int h, int w, int c8,
                                  int pad_lo, int ho, int wo, uint4* __restrict__ out) {
+  pdl_sync();
   const long long total = static_cast<long long>(nb) * ho * wo * 9 * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -94,6 +97,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ src, int nb, int h, i
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int nb, int c, int hw, int cpad,
                                     int coff, float scale, float shift,
                                     __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const long long total = static_cast<long long>(nb) * hw;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -106,6 +110,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int nb, int c
 }
 __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, int nb, int c, int hw, int ld,
                                         float scale, float* __restrict__ out) {
+  pdl_sync();
   const long long total = static_cast<long long>(nb) * hw * c;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -117,6 +122,7 @@ __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, int nb, i
 }
 __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int nb, int c, int hw, int ld,
                                         float scale, float* __restrict__ out) {
+  pdl_sync();
   const long long total = static_cast<long long>(nb) * c * hw;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -129,6 +135,7 @@ __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int nb, i
 }
 __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int nb, int c, int hw,
                                          int ld, float scale, float* __restrict__ out) {
+  pdl_sync();
   const long long total = static_cast<long long>(nb) * c * hw;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -167,6 +174,7 @@ __global__ void ddim_step_kernel(const float* __restrict__ mo, const float* __re
                                  int ptype, int clip, float clip_range, int use_clipped, float sigma,
                                  const float* __restrict__ noise, float* __restrict__ prev,
                                  float* __restrict__ x0o) {
+  pdl_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float pv, x0;
@@ -185,6 +193,7 @@ __global__ void sampler_step_kernel(const float4* __restrict__ eps, float4* __re
                                     int nsteps, int self_cond, const float* __restrict__ mask,
                                     const float4* __restrict__ known, const float4* __restrict__ noise,
                                     const float* __restrict__ sigma) {
+  pdl_sync();
   const int step = *step_ptr;
   const float sa_t = coef[step * 4 + 0], sb_t = coef[step * 4 + 1];
   const float sa_p = coef[step * 4 + 2], sb_p = coef[step * 4 + 3];
@@ -238,6 +247,7 @@ __global__ void advance_step_kernel(int* p) { *p = *p + 1; }
 // ---- time embedding -------------------------------------------------------------------------------
 __global__ void sinusoid_kernel(const float* __restrict__ t, int rows, int dim, int flip,
                                 float freq_shift, float* __restrict__ out) {
+  pdl_sync();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * half) return;
@@ -259,6 +269,7 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int rows, int dim, 
 __global__ void small_linear_kernel(const float* __restrict__ x, int rows, int k,
                                     const float* __restrict__ w, const float* __restrict__ b, int n,
                                     int silu_in, int silu_out, float* __restrict__ out, int out_ld) {
+  pdl_sync();
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= n) return;
@@ -295,6 +306,7 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int rows, int k
 // dst[b, :] = table[*step_ptr, :] for every image b (per-step time-embedding bias selection)
 __global__ void select_row_kernel(const float* __restrict__ table, int ncols,
                                   const int* __restrict__ step_ptr, int nb, float* __restrict__ dst) {
+  pdl_sync();
   const int step = *step_ptr;
   const long long total = static_cast<long long>(nb) * ncols;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -309,6 +321,7 @@ __global__ void ddim_step_indexed_kernel(const float* __restrict__ mo, const flo
                                          float final_alpha, int ptype, int clip, float clip_range,
                                          int use_clipped, float* __restrict__ prev,
                                          float* __restrict__ x0o) {
+  pdl_sync();
   const long long t = *t_ptr;
   const long long tp = t - step_ratio;
   const float a_t = acp[t];
@@ -330,6 +343,7 @@ template <bool kArgmax>
 __global__ void bilinear2x_kernel(const void* __restrict__ src, int src_is_f32, int nb, int h, int w,
                                   int c, int ld, float* __restrict__ out, uint8_t* __restrict__ ids,
                                   float* __restrict__ maxprob) {
+  pdl_sync();
   extern __shared__ float tile[];  // [2][34][c+1]
   const int cp = c + 1;
   const int xb = blockIdx.x * 32;          // first input column of this CTA's span
@@ -415,7 +429,7 @@ using namespace ldm;
 extern "C" int ldmseg_geglu(const void* x, int rows, int c, void* out, void* stream) {
   LDM_REQUIRE(x && out && c % 8 == 0, "geglu: bad arguments");
   const long long total = static_cast<long long>(rows) * (c / 8);
-  geglu_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(geglu_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), rows, c, reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("geglu_kernel");
 }
@@ -424,7 +438,7 @@ extern "C" int ldmseg_upsample2x(const void* src, int nb, int h, int w, int c, v
                                  void* stream) {
   LDM_REQUIRE(src && out && c % 8 == 0, "upsample2x: bad arguments");
   const long long total = static_cast<long long>(nb) * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(upsample2x_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), 
       reinterpret_cast<const uint4*>(src), nb, h, w, c / 8, reinterpret_cast<uint4*>(out));
   return check_launch("upsample2x_kernel");
 }
@@ -434,7 +448,7 @@ extern "C" int ldmseg_im2col_s2(const void* src, int nb, int h, int w, int c, in
   LDM_REQUIRE(src && out && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_s2: bad arguments");
   const int ho = h / 2, wo = w / 2;
   const long long total = static_cast<long long>(nb) * ho * wo * 9 * (c / 8);
-  im2col_s2_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(im2col_s2_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), 
       reinterpret_cast<const uint4*>(src), nb, h, w, c / 8, pad_lo, ho, wo,
       reinterpret_cast<uint4*>(out));
   return check_launch("im2col_s2_kernel");
@@ -444,7 +458,7 @@ extern "C" int ldmseg_nchw_to_nhwc_bf16(const float* src, int nb, int c, int hw,
                                         float scale, float shift, void* out, void* stream) {
   LDM_REQUIRE(src && out && coff + c <= cpad, "nchw_to_nhwc: bad arguments");
   const long long total = static_cast<long long>(nb) * hw;
-  nchw_to_nhwc_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(nchw_to_nhwc_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), 
       src, nb, c, hw, cpad, coff, scale, shift, reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("nchw_to_nhwc_kernel");
 }
@@ -453,7 +467,7 @@ extern "C" int ldmseg_nhwc_f32_to_nchw(const float* src, int nb, int c, int hw, 
                                        float* out, void* stream) {
   LDM_REQUIRE(src && out, "nhwc_f32_to_nchw: null pointer");
   const long long total = static_cast<long long>(nb) * c * hw;
-  nhwc_f32_to_nchw_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(src, nb, c, hw, ld, scale,
+  launch_kernel(nhwc_f32_to_nchw_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), src, nb, c, hw, ld, scale,
                                                                       out);
   return check_launch("nhwc_f32_to_nchw_kernel");
 }
@@ -462,7 +476,7 @@ extern "C" int ldmseg_nchw_f32_to_nhwc(const float* src, int nb, int c, int hw, 
                                        float* out, void* stream) {
   LDM_REQUIRE(src && out && ld >= c, "nchw_f32_to_nhwc: bad arguments");
   const long long total = static_cast<long long>(nb) * c * hw;
-  nchw_f32_to_nhwc_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(src, nb, c, hw, ld, scale, out);
+  launch_kernel(nchw_f32_to_nhwc_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), src, nb, c, hw, ld, scale, out);
   return check_launch("nchw_f32_to_nhwc_kernel");
 }
 
@@ -470,7 +484,7 @@ extern "C" int ldmseg_nhwc_bf16_to_nchw(const void* src, int nb, int c, int hw, 
                                         float* out, void* stream) {
   LDM_REQUIRE(src && out, "nhwc_bf16_to_nchw: null pointer");
   const long long total = static_cast<long long>(nb) * c * hw;
-  nhwc_bf16_to_nchw_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(nhwc_bf16_to_nchw_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), 
       reinterpret_cast<const __nv_bfloat16*>(src), nb, c, hw, ld, scale, out);
   return check_launch("nhwc_bf16_to_nchw_kernel");
 }
@@ -485,7 +499,7 @@ extern "C" int ldmseg_ddim_step(const float* model_out, const float* sample, int
   // the reference raises fp32 0-dim tensors to the power 0.5 (ddim_scheduler.py:240,264,267)
   const float sa_t = sqrtf(alpha_t), sb_t = sqrtf(1.f - alpha_t);
   const float sa_p = sqrtf(alpha_prev), sb_p = sqrtf(1.f - alpha_prev - sigma * sigma);
-  ddim_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(ddim_step_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, ST(stream), 
       model_out, sample, n, sa_t, sb_t, sa_p, sb_p, prediction_type, clip, clip_range, use_clipped,
       sigma, sigma > 0.f ? noise : nullptr, prev_sample, pred_x0);
   return check_launch("ddim_step_kernel");
@@ -499,7 +513,7 @@ extern "C" int ldmseg_sampler_step(const float* eps, float* latents, float* x0,
   LDM_REQUIRE(eps && latents && coef && step_ptr, "sampler_step: null pointer");
   LDM_REQUIRE(!unet_in || rgb_latents, "sampler_step: unet_in needs rgb_latents");
   LDM_REQUIRE(!mask || known, "sampler_step: mask needs known latents");
-  sampler_step_kernel<<<ew_grid(m, 128), 128, 0, ST(stream)>>>(
+  launch_kernel(sampler_step_kernel, dim3(ew_grid(m, 128)), dim3(128), 0, ST(stream), 
       reinterpret_cast<const float4*>(eps), reinterpret_cast<float4*>(latents),
       reinterpret_cast<float4*>(x0), reinterpret_cast<const float4*>(rgb_latents),
       reinterpret_cast<uint4*>(unet_in), m, coef, step_ptr, nsteps, self_cond, mask,
@@ -509,7 +523,7 @@ extern "C" int ldmseg_sampler_step(const float* eps, float* latents, float* x0,
 
 extern "C" int ldmseg_advance_step(int* step_ptr, void* stream) {
   LDM_REQUIRE(step_ptr, "advance_step: null pointer");
-  advance_step_kernel<<<1, 1, 0, ST(stream)>>>(step_ptr);
+  launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, ST(stream), step_ptr);
   return check_launch("advance_step_kernel");
 }
 
@@ -517,7 +531,7 @@ extern "C" int ldmseg_timestep_sinusoid(const float* t, int rows, int dim, int f
                                         float freq_shift, float* out, void* stream) {
   LDM_REQUIRE(t && out && dim % 2 == 0, "timestep_sinusoid: bad arguments");
   const int total = rows * (dim / 2);
-  sinusoid_kernel<<<(total + 127) / 128, 128, 0, ST(stream)>>>(t, rows, dim, flip_sin_to_cos,
+  launch_kernel(sinusoid_kernel, dim3((total + 127) / 128), dim3(128), 0, ST(stream), t, rows, dim, flip_sin_to_cos,
                                                               freq_shift, out);
   return check_launch("sinusoid_kernel");
 }
@@ -527,7 +541,7 @@ extern "C" int ldmseg_small_linear(const float* x, int rows, int k, const float*
                                    void* stream) {
   LDM_REQUIRE(x && w && out, "small_linear: null pointer");
   const int wpb = 4;
-  small_linear_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, ST(stream)>>>(x, rows, k, w, b, n, silu_in,
+  launch_kernel(small_linear_kernel, dim3((n + wpb - 1) / wpb), dim3(wpb * 32), 0, ST(stream), x, rows, k, w, b, n, silu_in,
                                                                         silu_out, out, out_ld);
   return check_launch("small_linear_kernel");
 }
@@ -536,7 +550,7 @@ extern "C" int ldmseg_select_row(const float* table, int ncols, const int* step_
                                  float* dst, void* stream) {
   LDM_REQUIRE(table && step_ptr && dst, "select_row: null pointer");
   const long long total = static_cast<long long>(nb) * ncols;
-  select_row_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(table, ncols, step_ptr, nb, dst);
+  launch_kernel(select_row_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), table, ncols, step_ptr, nb, dst);
   return check_launch("select_row_kernel");
 }
 
@@ -548,7 +562,7 @@ extern "C" int ldmseg_ddim_step_indexed(const float* model_out, const float* sam
   LDM_REQUIRE(model_out && sample && timestep_dev && alphas_cumprod_dev, "ddim_step_indexed: null pointer");
   LDM_REQUIRE(prediction_type >= 0 && prediction_type <= 2, "ddim_step_indexed: bad prediction_type");
   if (n == 0) return 0;
-  ddim_step_indexed_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+  launch_kernel(ddim_step_indexed_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, ST(stream), 
       model_out, sample, n, reinterpret_cast<const long long*>(timestep_dev), alphas_cumprod_dev,
       step_ratio, final_alpha, prediction_type, clip, clip_range, use_clipped, prev_sample, pred_x0);
   return check_launch("ddim_step_indexed_kernel");
@@ -566,7 +580,7 @@ static int launch_bilinear(bool argmax, const void* src, int src_is_f32, int nb,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 34 * 257 * 4));
       cfg = true;
     }
-    bilinear2x_kernel<true><<<grid, 64, smem, ST(stream)>>>(src, src_is_f32, nb, h, w, c, ld, nullptr,
+    launch_kernel(bilinear2x_kernel<true>, dim3(grid), dim3(64), smem, ST(stream), src, src_is_f32, nb, h, w, c, ld, nullptr,
                                                             ids, maxprob);
   } else {
     static bool cfg = false;
@@ -575,7 +589,7 @@ static int launch_bilinear(bool argmax, const void* src, int src_is_f32, int nb,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 34 * 257 * 4));
       cfg = true;
     }
-    bilinear2x_kernel<false><<<grid, 256, smem, ST(stream)>>>(src, src_is_f32, nb, h, w, c, ld, out,
+    launch_kernel(bilinear2x_kernel<false>, dim3(grid), dim3(256), smem, ST(stream), src, src_is_f32, nb, h, w, c, ld, out,
                                                               nullptr, nullptr);
   }
   return check_launch("bilinear2x_kernel");

@@ -48,9 +48,10 @@ struct alignas(64) IgemmKParams {
   int out_f32;
   int act;
   int split_k;
-  float* workspace;
-  int ws_ld;
+  float* workspace;   // split-K partial tiles: [tile][split][128][BN] f32
   int* counters;
+  float* stats;       // optional per-(image, channel) {sum, sum of squares} of the stored output
+  int stats_hw;       // rows per image for the statistics (the producer may be a plain [M, K] GEMM)
 };
 
 template <int BN>
@@ -59,97 +60,141 @@ struct IgemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 160) ? 5 : 4;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  // stages + barriers (2*stages + 4) * 8 + tmem ptr + split-K flag, + 1024 alignment slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+  static constexpr int kStagingBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 32 f32
+  // stages + epilogue staging + barriers (2*stages + 4) * 8 + tmem ptr + split-K flag, + 1024 slack
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStagingBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
-// Applies the epilogue to 32 consecutive output columns [n, n+32) of row m and stores them.
-__device__ __forceinline__ void epilogue_store32(const IgemmKParams& p, float (&v)[32], int m,
-                                                 int n) {
-  if (p.bias != nullptr) {
+// ---- epilogue ------------------------------------------------------------------------------
+// A warp owns 32 accumulator rows (its TMEM lane quadrant).  tcgen05.ld hands every thread ONE row
+// (32 consecutive f32 columns); storing that directly would touch 32 different lines per
+// instruction.  The chunk is therefore transposed through a 4 KB per-warp staging buffer
+// (XOR-swizzled 16-byte slots, conflict-free both ways): afterwards lane l holds columns
+// 4*(l&7)..+3 of row 4*i + (l>>3), i = 0..7, so 8 lanes cover 128 contiguous bytes of a row and all
+// global accesses (output, residual, split-K partials) are coalesced.
+enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2 };
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_warp(const IgemmKParams& p, uint8_t* stg, uint32_t t_row,
+                                              float* ws_tile, int split_idx, int m_base, int n0,
+                                              int lane) {
+  const int jc = lane & 7;    // 16-byte column slot inside the 32-column chunk
+  const int rsub = lane >> 3;  // row within a group of 4
+  constexpr int kTileElems = BM * BN;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    if (n0 + c >= p.N) break;
+    if (MODE != EPI_FINAL) {
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + c, r);
+      tmem_wait_ld();
+      float4* rowp = reinterpret_cast<float4*>(stg + lane * 128);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
-  }
-  if (p.rowbias != nullptr) {
-    const float* rb = p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < p.N) v[j] += __ldg(rb + n + j);
-  }
-  if (p.act == LDMSEG_ACT_GEGLU) {
-    // columns come interleaved per 32: [16 x h | 16 x g]; output column = n/2 + i
-    float o[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = v[i] * gelu_erf_f(v[16 + i]);
-    const int no = n >> 1;
-    if (n < p.N) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                           static_cast<size_t>(m) * p.out_ld + no;
-      uint4 a, b;
-      a.x = pack_bf16x2(o[0], o[1]);
-      a.y = pack_bf16x2(o[2], o[3]);
-      a.z = pack_bf16x2(o[4], o[5]);
-      a.w = pack_bf16x2(o[6], o[7]);
-      b.x = pack_bf16x2(o[8], o[9]);
-      b.y = pack_bf16x2(o[10], o[11]);
-      b.z = pack_bf16x2(o[12], o[13]);
-      b.w = pack_bf16x2(o[14], o[15]);
-      reinterpret_cast<uint4*>(dst)[0] = a;
-      reinterpret_cast<uint4*>(dst)[1] = b;
+      for (int j = 0; j < 8; ++j)
+        rowp[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
     }
-    return;
-  }
-  if (p.residual != nullptr) {
-    const __nv_bfloat16* r = p.residual + static_cast<size_t>(m) * p.res_ld + n;
+    const int col = n0 + c + jc * 4;
+    const bool col_ok = col < p.N;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE != EPI_PARTIAL && p.bias != nullptr && col_ok)
+      bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    float4 s_sum = make_float4(0.f, 0.f, 0.f, 0.f), s_sq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (n + g * 8 + 8 <= p.N) {
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(r) + g);
-        float2 f;
-        f = unpack_bf16x2(u.x); v[g * 8 + 0] += f.x; v[g * 8 + 1] += f.y;
-        f = unpack_bf16x2(u.y); v[g * 8 + 2] += f.x; v[g * 8 + 3] += f.y;
-        f = unpack_bf16x2(u.z); v[g * 8 + 4] += f.x; v[g * 8 + 5] += f.y;
-        f = unpack_bf16x2(u.w); v[g * 8 + 6] += f.x; v[g * 8 + 7] += f.y;
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + rsub;
+      const int m = m_base + row;
+      const bool ok = col_ok && m < p.M;
+      float4 v;
+      if (MODE == EPI_FINAL) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          const float* src = ws_tile + (m - (m_base & ~(BM - 1))) * BN + c + jc * 4;
+          for (int sidx = 0; sidx < p.split_k; ++sidx)
+            v = f4_add(v, __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(sidx) * kTileElems)));
+        }
       } else {
-        for (int j = g * 8; j < g * 8 + 8; ++j)
-          if (n + j < p.N) v[j] += __bfloat162float(r[j]);
+        v = reinterpret_cast<const float4*>(stg + row * 128)[jc ^ (row & 7)];
+      }
+      if (MODE == EPI_PARTIAL) {
+        if (ok)
+          *reinterpret_cast<float4*>(ws_tile + static_cast<size_t>(split_idx) * kTileElems +
+                                     (m - (m_base & ~(BM - 1))) * BN + c + jc * 4) = v;
+        continue;
+      }
+      v = f4_add(v, bias4);
+      if (p.rowbias != nullptr && ok)
+        v = f4_add(v, __ldg(reinterpret_cast<const float4*>(
+                          p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld + col)));
+      if (p.act == LDMSEG_ACT_GEGLU) {
+        // chunk columns are [16 x h | 16 x g]: slots 0..3 hold h, slots 4..7 the matching g
+        float4 g;
+        g.x = __shfl_xor_sync(0xffffffffu, v.x, 4);
+        g.y = __shfl_xor_sync(0xffffffffu, v.y, 4);
+        g.z = __shfl_xor_sync(0xffffffffu, v.z, 4);
+        g.w = __shfl_xor_sync(0xffffffffu, v.w, 4);
+        if (ok && jc < 4) {
+          uint2 u;
+          u.x = pack_bf16x2(v.x * gelu_erf_f(g.x), v.y * gelu_erf_f(g.y));
+          u.y = pack_bf16x2(v.z * gelu_erf_f(g.z), v.w * gelu_erf_f(g.w));
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                    static_cast<size_t>(m) * p.out_ld + ((n0 + c) >> 1) + jc * 4) = u;
+        }
+        continue;
+      }
+      if (p.residual != nullptr && ok) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.residual + static_cast<size_t>(m) * p.res_ld + col));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+      }
+      if (p.act == LDMSEG_ACT_SILU) {
+        v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+      }
+      if (p.out_f32) {
+        if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = v;
+      } else {
+        uint2 u;
+        u.x = pack_bf16x2(v.x, v.y);
+        u.y = pack_bf16x2(v.z, v.w);
+        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = u;
+        if (p.stats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          v = make_float4(a.x, a.y, b.x, b.y);
+        }
+      }
+      if (p.stats != nullptr && ok) {
+        s_sum = f4_add(s_sum, v);
+        s_sq = f4_add(s_sq, make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
       }
     }
-  }
-  if (p.act == LDMSEG_ACT_SILU) {
+    if (MODE != EPI_PARTIAL && p.stats != nullptr) {
+      // column sums over the warp's 32 rows (all in one image: HW % 32 == 0 is validated on the host)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-  }
-  if (p.out_f32) {
-    float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (n + g * 4 + 4 <= p.N) {
-        reinterpret_cast<float4*>(dst)[g] =
-            make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      } else {
-        for (int j = g * 4; j < g * 4 + 4; ++j)
-          if (n + j < p.N) dst[j] = v[j];
+      for (int o = 8; o <= 16; o <<= 1) {
+        s_sum.x += __shfl_xor_sync(0xffffffffu, s_sum.x, o);
+        s_sum.y += __shfl_xor_sync(0xffffffffu, s_sum.y, o);
+        s_sum.z += __shfl_xor_sync(0xffffffffu, s_sum.z, o);
+        s_sum.w += __shfl_xor_sync(0xffffffffu, s_sum.w, o);
+        s_sq.x += __shfl_xor_sync(0xffffffffu, s_sq.x, o);
+        s_sq.y += __shfl_xor_sync(0xffffffffu, s_sq.y, o);
+        s_sq.z += __shfl_xor_sync(0xffffffffu, s_sq.z, o);
+        s_sq.w += __shfl_xor_sync(0xffffffffu, s_sq.w, o);
+      }
+      if (rsub == 0 && col_ok && m_base < p.M) {
+        float* st = p.stats + (static_cast<size_t>(m_base / p.stats_hw) * p.N + col) * 2;
+        atomicAdd(st + 0, s_sum.x); atomicAdd(st + 1, s_sq.x);
+        atomicAdd(st + 2, s_sum.y); atomicAdd(st + 3, s_sq.y);
+        atomicAdd(st + 4, s_sum.z); atomicAdd(st + 5, s_sq.z);
+        atomicAdd(st + 6, s_sum.w); atomicAdd(st + 7, s_sq.w);
       }
     }
-  } else {
-    __nv_bfloat16* dst =
-        reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + n;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (n + g * 8 + 8 <= p.N) {
-        uint4 u;
-        u.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-        u.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-        u.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-        u.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-        reinterpret_cast<uint4*>(dst)[g] = u;
-      } else {
-        for (int j = g * 8; j < g * 8 + 8; ++j)
-          if (n + j < p.N) dst[j] = __float2bfloat16(v[j]);
-      }
-    }
+    if (MODE != EPI_FINAL) __syncwarp();
   }
 }
 
@@ -164,7 +209,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -195,6 +241,9 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here
+  // on we touch memory it produced.  (No-ops when the launch carries no PDL attribute.)
+  pdl_sync();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int total_work = num_tiles * p.split_k;
@@ -295,50 +344,29 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = threadIdx.x - 64;  // 0..127
+    uint8_t* stg = smem_stg + q * (32 * 128);
     int it = 0;
     for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
       const int tile = wi / p.split_k;
+      const int split = wi - tile * p.split_k;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m = m_tile * BM + q * 32 + lane;
+      const int m_base = m_tile * BM + q * 32;
       const int n0 = n_tile * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (p.split_k <= 1) {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (n0 + c >= p.N) break;
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + c, r);
-          tmem_wait_ld();
-          if (m < p.M) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_store32(p, v, m, n0 + c);
-          }
-        }
+        epilogue_warp<BN, EPI_DIRECT>(p, stg, t_row, nullptr, 0, m_base, n0, lane);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       } else {
-        // split-K: accumulate the partial tile into the f32 workspace; the last CTA to finish a
-        // tile applies the epilogue and re-zeroes the workspace (ready for the next launch).
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (n0 + c >= p.N) break;
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + c, r);
-          tmem_wait_ld();
-          if (m < p.M) {
-            float* ws = p.workspace + static_cast<size_t>(m) * p.ws_ld + n0 + c;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c + j < p.N) atomicAdd(ws + j, __uint_as_float(r[j]));
-          }
-        }
+        // split-K: every split stores its partial tile (coalesced, no atomics); the CTA that
+        // arrives last sums the partials and applies the epilogue.
+        float* ws_tile = p.workspace + static_cast<size_t>(tile) * p.split_k * (BM * BN);
+        epilogue_warp<BN, EPI_PARTIAL>(p, stg, t_row, ws_tile, split, m_base, n0, lane);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
         __threadfence();
@@ -352,24 +380,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         const int is_last = *is_last_smem;
         if (is_last) {
           __threadfence();
-          if (m < p.M) {
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-              if (n0 + c >= p.N) break;
-              float* ws = p.workspace + static_cast<size_t>(m) * p.ws_ld + n0 + c;
-              float v[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (n0 + c + j < p.N) {
-                  v[j] = __ldcg(ws + j);
-                  ws[j] = 0.f;
-                } else {
-                  v[j] = 0.f;
-                }
-              }
-              epilogue_store32(p, v, m, n0 + c);
-            }
-          }
+          epilogue_warp<BN, EPI_FINAL>(p, stg, 0, ws_tile, 0, m_base, n0, lane);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -387,6 +398,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
 // ------------------------------------------------------------------------------------------
 // Reference-grade CUDA-core kernel with the same contract (one thread per output element).
 __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
+  pdl_sync();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int ncols = p.n;
   if (idx >= static_cast<long long>(M) * ncols) return;
@@ -437,11 +449,18 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
     acc += __bfloat162float(
         reinterpret_cast<const __nv_bfloat16*>(p.residual)[static_cast<size_t>(m) * p.res_ld + n]);
   if (p.act == LDMSEG_ACT_SILU) acc = silu_f(acc);
-  if (p.out_dtype == LDMSEG_OUT_F32)
+  if (p.out_dtype == LDMSEG_OUT_F32) {
     reinterpret_cast<float*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] = acc;
-  else
-    reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] =
-        __float2bfloat16(acc);
+  } else {
+    const __nv_bfloat16 o = __float2bfloat16(acc);
+    reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] = o;
+    acc = __bfloat162float(o);
+  }
+  if (p.stats) {
+    const int sb = p.stats_hw > 0 ? m / p.stats_hw : b;
+    atomicAdd(p.stats + (static_cast<size_t>(sb) * p.n + n) * 2, acc);
+    atomicAdd(p.stats + (static_cast<size_t>(sb) * p.n + n) * 2 + 1, acc * acc);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,15 +500,21 @@ static int validate(const ldmseg_igemm_params* p) {
     LDM_REQUIRE(p->out_ld % 8 == 0, "igemm: GEGLU out_ld must be a multiple of 8");
   }
   if (p->out_dtype == LDMSEG_OUT_BF16 && p->act != LDMSEG_ACT_GEGLU)
-    LDM_REQUIRE(p->out_ld % 8 == 0 || p->n < 8, "igemm: bf16 out_ld must be a multiple of 8");
+    LDM_REQUIRE(p->out_ld % 4 == 0, "igemm: bf16 out_ld must be a multiple of 4");
   if (p->out_dtype == LDMSEG_OUT_F32)
     LDM_REQUIRE(p->out_ld % 4 == 0, "igemm: f32 out_ld must be a multiple of 4");
-  if (p->residual) LDM_REQUIRE(p->res_ld % 8 == 0, "igemm: res_ld must be a multiple of 8");
+  if (p->residual) LDM_REQUIRE(p->res_ld % 4 == 0, "igemm: res_ld must be a multiple of 4");
+  LDM_REQUIRE(p->n % 4 == 0, "igemm: n must be a multiple of 4 (got %d)", p->n);
+  if (p->rowbias) LDM_REQUIRE(p->rowbias_ld % 4 == 0, "igemm: rowbias_ld must be a multiple of 4");
+  if (p->stats) {
+    LDM_REQUIRE((p->stats_hw > 0 ? p->stats_hw : hw) % 32 == 0, "igemm: fused statistics need rows per image %% 32 == 0");
+    LDM_REQUIRE(p->act != LDMSEG_ACT_GEGLU, "igemm: fused statistics are not defined for GEGLU");
+  }
   return 0;
 }
 
 template <int BN>
-static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream) {
+static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   using Cfg = IgemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -497,7 +522,22 @@ static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream) {
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  igemm_kernel<BN><<<grid, kIgemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kIgemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl || g_pdl) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN>, kp);
+  if (e != cudaSuccess) {
+    set_error("igemm_kernel launch: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
   return check_launch("igemm_kernel");
 }
 
@@ -584,18 +624,22 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   if (kp.split_k > 1) {
     LDM_REQUIRE(p->workspace != nullptr && p->tile_counters != nullptr,
                 "igemm: split_k > 1 needs workspace and tile_counters");
+    const long long need = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k * BM * bn;
+    LDM_REQUIRE(p->workspace_elems >= need, "igemm: split-K workspace too small (%lld f32 needed, %lld given)",
+                need, static_cast<long long>(p->workspace_elems));
     kp.workspace = p->workspace;
-    kp.ws_ld = (p->n + 3) / 4 * 4;
     kp.counters = p->tile_counters;
   }
+  kp.stats = p->stats;
+  kp.stats_hw = p->stats_hw > 0 ? p->stats_hw : HW;
   const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
   const int grid = static_cast<int>(work < num_sms() ? work : num_sms());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 64: return launch_igemm<64>(kp, grid, st);
-    case 128: return launch_igemm<128>(kp, grid, st);
-    case 160: return launch_igemm<160>(kp, grid, st);
-    default: return launch_igemm<256>(kp, grid, st);
+    case 64: return launch_igemm<64>(kp, grid, st, p->pdl);
+    case 128: return launch_igemm<128>(kp, grid, st, p->pdl);
+    case 160: return launch_igemm<160>(kp, grid, st, p->pdl);
+    default: return launch_igemm<256>(kp, grid, st, p->pdl);
   }
 }
 
@@ -605,7 +649,7 @@ extern "C" int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream) {
   const long long total = static_cast<long long>(M) * p->n;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  igemm_simple_kernel<<<static_cast<unsigned>(blocks), threads, 0,
-                        reinterpret_cast<cudaStream_t>(stream)>>>(*p, M, p->h * p->w);
+  launch_kernel(igemm_simple_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0,
+                reinterpret_cast<cudaStream_t>(stream), *p, M, p->h * p->w);
   return check_launch("igemm_simple_kernel");
 }

@@ -37,6 +37,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ s0, int c0,
                                 const __nv_bfloat16* __restrict__ s1, int c1, int hw,
                                 int pix_per_cta, int groups, float* __restrict__ stats) {
+  pdl_sync();
   __shared__ float sg[2 * 64];
   const int C = c0 + c1;
   const int cpg = C / groups;
@@ -97,6 +98,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ s0, int c0,
                                 int pix_per_cta, int groups, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float eps, int silu, __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int C = c0 + c1;
   float* scale = sm;
@@ -142,6 +144,7 @@ template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ src, int rows, int c,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, int silu, __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -204,6 +207,7 @@ __global__ void convt_shuffle_ln_kernel(const __nv_bfloat16* __restrict__ src, i
                                         int c, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, float eps, int silu,
                                         __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(nb) * h * w * 4;
@@ -268,6 +272,7 @@ __global__ void convt_shuffle_ln_kernel(const __nv_bfloat16* __restrict__ src, i
 // (diffusers 0.16.1 AttentionBlock: softmax in fp32 over baddbmm scores).
 __global__ void softmax_rows_kernel(const float* __restrict__ s, int cols, float scale,
                                     __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[32];
   const float* row = s + static_cast<size_t>(blockIdx.x) * cols;
   __nv_bfloat16* orow = out + static_cast<size_t>(blockIdx.x) * cols;
@@ -313,7 +318,7 @@ using namespace ldm;
 extern "C" int ldmseg_softmax_rows(const float* s, int rows, int cols, float scale, void* out,
                                    void* stream) {
   LDM_REQUIRE(s && out && cols % 4 == 0, "softmax_rows: bad arguments");
-  softmax_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(softmax_rows_kernel, dim3(rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       s, cols, scale, reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("softmax_rows_kernel");
 }
@@ -340,7 +345,7 @@ extern "C" int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int 
   int ppc = (hw + chunks - 1) / chunks;
   chunks = (hw + ppc - 1) / ppc;
   dim3 grid(chunks, nb), block(C8, py);
-  gn_stats_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src0), c0,
+  launch_kernel(gn_stats_kernel, dim3(grid), dim3(block), 0, st, reinterpret_cast<const __nv_bfloat16*>(src0), c0,
                                           reinterpret_cast<const __nv_bfloat16*>(src1), c1, hw, ppc,
                                           groups, stats);
   if (int rc = check_launch("gn_stats_kernel")) return rc;
@@ -352,7 +357,7 @@ extern "C" int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int 
   int appc = (hw + achunks - 1) / achunks;
   achunks = (hw + appc - 1) / appc;
   dim3 agrid(achunks, nb);
-  gn_apply_kernel<<<agrid, 256, 2 * C * sizeof(float), st>>>(
+  launch_kernel(gn_apply_kernel, dim3(agrid), dim3(256), 2 * C * sizeof(float), st, 
       reinterpret_cast<const __nv_bfloat16*>(src0), c0, reinterpret_cast<const __nv_bfloat16*>(src1),
       c1, hw, appc, groups, stats, gamma, beta, eps, silu, reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("gn_apply_kernel");
@@ -368,11 +373,11 @@ extern "C" int ldmseg_layernorm(const void* src, int rows, int c, const float* g
   const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (c <= 512)
-    layernorm_kernel<2><<<grid, wpb * 32, 0, st>>>(s, rows, c, gamma, beta, eps, silu, o);
+    launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(wpb * 32), 0, st, s, rows, c, gamma, beta, eps, silu, o);
   else if (c <= 1280)
-    layernorm_kernel<5><<<grid, wpb * 32, 0, st>>>(s, rows, c, gamma, beta, eps, silu, o);
+    launch_kernel(layernorm_kernel<5>, dim3(grid), dim3(wpb * 32), 0, st, s, rows, c, gamma, beta, eps, silu, o);
   else
-    layernorm_kernel<8><<<grid, wpb * 32, 0, st>>>(s, rows, c, gamma, beta, eps, silu, o);
+    launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, st, s, rows, c, gamma, beta, eps, silu, o);
   return check_launch("layernorm_kernel");
 }
 
@@ -384,8 +389,7 @@ extern "C" int ldmseg_convt_shuffle_ln(const void* src, int nb, int h, int w, in
   const long long warps = static_cast<long long>(nb) * h * w * 4;
   const int wpb = 8;
   const long long grid = (warps + wpb - 1) / wpb;
-  convt_shuffle_ln_kernel<<<static_cast<unsigned>(grid), wpb * 32, 0,
-                            reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(convt_shuffle_ln_kernel, dim3(static_cast<unsigned>(grid)), dim3(wpb * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(src), nb, h, w, c, gamma, beta, eps, silu,
       reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("convt_shuffle_ln_kernel");

@@ -236,6 +236,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// First statement of every kernel that reads memory written by its stream predecessor.  `wait`
+// blocks until all prerequisite grids have completed and their writes are visible; the trigger lets
+// the NEXT kernel's CTAs be scheduled (they block at their own wait).  Both are no-ops without PDL.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -28,6 +28,7 @@ EXPORTS = [
     "ldmseg_ddim_step", "ldmseg_sampler_step", "ldmseg_advance_step", "ldmseg_timestep_sinusoid",
     "ldmseg_small_linear", "ldmseg_convt_shuffle_ln", "ldmseg_bilinear2x_to_nchw",
     "ldmseg_bilinear2x_argmax", "ldmseg_select_row", "ldmseg_ddim_step_indexed", "ldmseg_softmax_rows", "ldmseg_nchw_f32_to_nhwc",
+    "ldmseg_groupnorm_apply_cs", "ldmseg_set_pdl",
 ]
 
 
@@ -56,6 +57,10 @@ class IgemmParams(C.Structure):
         ("split_k", C.c_int),
         ("workspace", C.c_void_p),
         ("tile_counters", C.c_void_p),
+        ("workspace_elems", C.c_longlong),
+        ("stats", C.c_void_p),
+        ("stats_hw", C.c_int),
+        ("pdl", C.c_int),
     ]
 
 
@@ -103,6 +108,8 @@ def load() -> C.CDLL:
         "ldmseg_bilinear2x_to_nchw": [vp, i32, i32, i32, i32, i32, i32, vp, vp],
         "ldmseg_bilinear2x_argmax": [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp],
         "ldmseg_select_row": [vp, i32, vp, i32, vp, vp],
+        "ldmseg_groupnorm_apply_cs": [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, vp, vp],
+        "ldmseg_set_pdl": [i32],
         "ldmseg_softmax_rows": [vp, i32, i32, f32, vp, vp],
         "ldmseg_ddim_step_indexed": [vp, vp, i64, vp, vp, i32, f32, i32, i32, f32, i32, vp, vp, vp],
     }
@@ -147,7 +154,8 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
                       residual: Optional[torch.Tensor] = None, res_ld: int = 0, act: int = ACT_NONE,
                       block_n: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
-                      counters: Optional[torch.Tensor] = None) -> IgemmParams:
+                      counters: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+                      stats_hw: int = 0, pdl: bool = False) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -177,6 +185,10 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.split_k = split_k
     p.workspace = _ptr(workspace)
     p.tile_counters = _ptr(counters)
+    p.workspace_elems = workspace.numel() if workspace is not None else 0
+    p.stats = _ptr(stats)
+    p.stats_hw = stats_hw
+    p.pdl = int(pdl)
     return p
 
 
@@ -298,3 +310,14 @@ def softmax_rows(s, rows, cols, scale, out) -> None:
 def nchw_f32_to_nhwc(src, nb, c, hw, ld, scale, out) -> None:
     _check(load().ldmseg_nchw_f32_to_nhwc(_ptr(src), nb, c, hw, ld, scale, _ptr(out), _stream()),
            "ldmseg_nchw_f32_to_nhwc")
+
+
+def groupnorm_apply_cs(src0, c0, cs0, src1, c1, cs1, nb, hw, groups, gamma, beta, eps, silu, out) -> None:
+    _check(load().ldmseg_groupnorm_apply_cs(_ptr(src0), c0, _ptr(cs0), _ptr(src1), c1, _ptr(cs1), nb, hw, groups,
+                                            _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(out), _stream()),
+           "ldmseg_groupnorm_apply_cs")
+
+
+def set_pdl(enable: bool) -> bool:
+    """Enable programmatic dependent launch for every kernel of the library; returns the old setting."""
+    return bool(load().ldmseg_set_pdl(int(enable)))

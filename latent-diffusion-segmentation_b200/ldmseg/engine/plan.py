@@ -3,6 +3,7 @@ helpers that append kernel launches (igemm / GroupNorm / LayerNorm / resnet bloc
 channel-last buffers."""
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -11,30 +12,39 @@ from ldmseg import _native as nat
 from ldmseg import _pack as pk
 
 SMS = 148
+# measured on B200 (tools/bench_igemm.py): operand ingest of one SM sustains ~59 B/cycle, i.e. one
+# 128-byte swizzle row of a TMA box every ~2.17 cycles; an M=128 x N=bn x K=16 tcgen05.mma takes bn/2 cycles
+CYC_PER_TMA_ROW = 2.17
+USE_PDL = os.environ.get("LDMSEG_PDL", "1") != "0"
+FUSE_GN_STATS = os.environ.get("LDMSEG_FUSE_GN_STATS", "1") != "0"
 
 
-def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS) -> Tuple[int, int]:
+def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True) -> Tuple[int, int]:
     """Pick (block_n, split_k) for an igemm of M x N with num_kb 64-wide K blocks.
 
-    Cost model (arbitrary units = MMA column-steps): a work item costs
-    kb_per_split * max(block_n, 96) + a fixed fill/epilogue overhead; items run in waves of `sms`.
-    Split-K is only considered when the tiles alone cannot fill the machine."""
+    Cycle model per work item (one CTA, one output tile, one K split):
+        k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + bn))  +  prologue  +  epilogue
+    items run in waves of `sms` CTAs.  Split-K (partials to a workspace, last CTA reduces) is considered
+    only when the tiles cannot fill the machine, and is charged for the partial store and the reduction."""
     m_tiles = (m + 127) // 128
-    best = (128, 1)
-    best_cost = float("inf")
+    best, best_cost = (128, 1), float("inf")
     for bn in (256, 160, 128, 64):
         tiles = m_tiles * ((n + bn - 1) // bn)
+        t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + bn))
+        chunks = bn / 32.0
         splits = [1]
-        if tiles < sms:
+        if allow_split and tiles < sms:
             s = 2
-            while tiles * s <= sms and num_kb // s >= 4 and s <= 32:
+            while tiles * s <= sms and num_kb // s >= 3 and s <= 24:
                 splits.append(s)
                 s += 1
         for s in splits:
             waves = (tiles * s + sms - 1) // sms
             kb = (num_kb + s - 1) // s
-            fixed = 24 * bn / 64 + 16 + (10 * bn / 64 if s > 1 else 0)
-            cost = waves * (kb * max(bn, 96) / 64.0 + fixed)
+            item = kb * t_kb + 1500 + chunks * 250
+            if s > 1:
+                item += chunks * 200 + s * chunks * 160 + 600
+            cost = waves * item
             if cost < best_cost - 1e-9:
                 best_cost, best = cost, (bn, s)
     return best
@@ -46,8 +56,6 @@ class _Layer:
 
     def __init__(self, w, bias, n, **extra):
         self.w, self.bias, self.n, self.extra = w, bias, n, extra
-
-
 
 
 class WeightsBase:
@@ -83,7 +91,11 @@ class WeightsBase:
 
 
 class PlanBase:
-    """Static launch list + buffers.  Subclasses fill `self.ops` in `_build`."""
+    """Static launch list + buffers.  Subclasses fill `self.ops` in `_build`.
+
+    GroupNorm statistics are fused into the producing igemm whenever the GroupNorm input was written by
+    an igemm of this plan: `_gn` then assigns that producer a slice of `stats_arena` (per-image,
+    per-channel sum / sum of squares, zeroed once per run) and emits a single apply kernel."""
 
     def __init__(self, W: WeightsBase, nb: int):
         self.W, self.nb = W, nb
@@ -91,10 +103,17 @@ class PlanBase:
         self.ops: List[Callable[[], None]] = []
         self.n_launch = 0
         self._keep: list = []
-        self.ws = torch.zeros(8 * 1024 * 1024, device=self.device, dtype=torch.float32)  # split-K partials
+        self.ws = torch.zeros(16 * 1024 * 1024, device=self.device, dtype=torch.float32)  # split-K partials
         self.counters = torch.zeros(8192, device=self.device, dtype=torch.int32)
         self.gn_stats = torch.zeros(nb * 64 * 2, device=self.device, dtype=torch.float32)
+        self.stats_arena = torch.zeros(nb * 512 * 1024, device=self.device, dtype=torch.float32)
+        self._arena_used = 0
+        self._producer: Dict[int, tuple] = {}   # out.data_ptr() -> (IgemmParams, n, rows_per_image)
+        self._chan_stats: Dict[int, torch.Tensor] = {}
         self.rowbias_ld = 0
+        self.pdl = USE_PDL
+        arena = self.stats_arena
+        self._op(lambda: arena.zero_(), 1)
 
     def _buf(self, rows, c, dtype=torch.bfloat16):
         t = torch.empty(rows, c, device=self.device, dtype=dtype)
@@ -108,23 +127,54 @@ class PlanBase:
     def _gemm(self, layer: _Layer, srcs, src_c, nb, h, w, segs, out, *, rowbias=None, residual=None,
               act=nat.ACT_NONE, out_ld=None, bias="layer", allow_split=True):
         num_kb = sum(taps * ((src_c[s] + 63) // 64) for s, taps in segs)
-        bn, split = choose_tiling(nb * h * w, layer.n, num_kb)
-        ws_need = nb * h * w * ((layer.n + 3) // 4 * 4)
-        if split > 1 and (ws_need > self.ws.numel() or not allow_split):
-            split = 1
+        m = nb * h * w
+        bn, split = choose_tiling(m, layer.n, num_kb, allow_split=allow_split)
+        tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
+        if split > 1 and tiles * split * 128 * bn > self.ws.numel():
+            bn, split = choose_tiling(m, layer.n, num_kb, allow_split=False)
         p = nat.make_igemm_params(srcs, src_c, nb, h, w, segs, layer.w, layer.n, out,
                                   out_ld if out_ld is not None else out.shape[1],
                                   bias=layer.bias if bias == "layer" else bias,
                                   rowbias=rowbias, rowbias_ld=self.rowbias_ld if rowbias is not None else 0,
                                   residual=residual, res_ld=residual.shape[1] if residual is not None else 0,
-                                  act=act, block_n=bn, split_k=split, workspace=self.ws, counters=self.counters)
+                                  act=act, block_n=bn, split_k=split, workspace=self.ws, counters=self.counters,
+                                  pdl=self.pdl)
         self._keep.append(p)
+        if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
+            self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
         self._op(lambda p=p: nat.igemm(p))
+
+    def _stats_for(self, src, c, hw) -> Optional[torch.Tensor]:
+        """Channel-statistics slice for a GroupNorm source written by an igemm of this plan (or None)."""
+        if not FUSE_GN_STATS or hw % 32 != 0:
+            return None
+        key = src.data_ptr()
+        if key in self._chan_stats:
+            return self._chan_stats[key]
+        prod = self._producer.get(key)
+        if prod is None or prod[1] != c or prod[2] != self.nb * hw:
+            return None
+        need = self.nb * c * 2
+        if self._arena_used + need > self.stats_arena.numel():
+            return None
+        sl = self.stats_arena[self._arena_used:self._arena_used + need]
+        self._arena_used += need
+        prod[0].stats = sl.data_ptr()          # the producer's launch happens later, at run time
+        prod[0].stats_hw = hw
+        self._chan_stats[key] = sl
+        return sl
 
     def _gn(self, name, src0, c0, src1, c1, hw, silu, out):
         g, b, eps = self.W.norms[name]
-        nb, groups, stats = self.nb, self.W.groups, self.gn_stats
-        self._op(lambda: nat.groupnorm(src0, c0, src1, c1, nb, hw, groups, g, b, eps, silu, out, stats), 2)
+        nb, groups = self.nb, self.W.groups
+        cs0 = self._stats_for(src0, c0, hw)
+        cs1 = self._stats_for(src1, c1, hw) if src1 is not None else None
+        if cs0 is not None and (src1 is None or cs1 is not None):
+            self._op(lambda: nat.groupnorm_apply_cs(src0, c0, cs0, src1, c1, cs1, nb, hw, groups, g, b, eps, silu,
+                                                    out))
+            return
+        stats = self.gn_stats
+        self._op(lambda: nat.groupnorm(src0, c0, src1, c1, nb, hw, groups, g, b, eps, silu, out, stats), 3)
 
     def _ln(self, name, src, rows, c, out, silu=False):
         g, b, eps = self.W.norms[name]
@@ -155,5 +205,9 @@ class PlanBase:
         return out
 
     def run(self) -> None:
-        for op in self.ops:
-            op()
+        old = nat.set_pdl(self.pdl)
+        try:
+            for op in self.ops:
+                op()
+        finally:
+            nat.set_pdl(old)

@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "norm", "attn_simple",
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "gn_fused", "norm", "attn_simple",
           "attn", "elementwise"]
 
 
@@ -46,7 +46,7 @@ def run_group(group):
 
     def conv_case(name, nb, h, w, cin, cout, *, taps=9, bias=True, residual=False, rowbias=False,
                   act=nat.ACT_NONE, out_f32=False, block_n=0, split_k=0, simple=False, extra_src=None,
-                  shortcut=False):
+                  shortcut=False, stats=False, pdl=False):
         """out = conv(x (+ extra_src concat)) [+ 1x1 shortcut of the raw sources] ..."""
         nonlocal ok
         srcs_c = [cin] + ([extra_src] if extra_src else [])
@@ -81,13 +81,16 @@ def run_group(group):
                          dtype=torch.float32 if out_f32 else bf)
         ws = cnt = None
         if split_k > 1:
-            ws = torch.zeros((nb * h * w + 128) * ((cout + 3) // 4 * 4), device=dev)
+            ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev)   # partials are overwritten, never read stale
             cnt = torch.zeros(4096, device=dev, dtype=torch.int32)
+        st = torch.zeros(nb, cout, 2, device=dev) if stats else None
         p = nat.make_igemm_params(srcs, src_cs, nb, h, w, segs, wb, cout, out, n_out, bias=b,
                                   rowbias=rb, rowbias_ld=cout, residual=res, res_ld=cout, act=act,
-                                  block_n=block_n, split_k=split_k, workspace=ws, counters=cnt)
+                                  block_n=block_n, split_k=split_k, workspace=ws, counters=cnt, stats=st, pdl=pdl)
         nat.igemm(p, simple=simple)
-        if split_k > 1:  # second launch must see a clean (self-zeroed) workspace
+        if split_k > 1:  # second launch: tile counters must have reset themselves
+            if st is not None:
+                st.zero_()
             nat.igemm(p, simple=simple)
         torch.cuda.synchronize()
         # reference in fp32 from the bf16-rounded operands
@@ -112,8 +115,12 @@ def run_group(group):
         if act == nat.ACT_SILU:
             ref = F.silu(ref)
         ok &= report(name, out, ref, 1e-2 if not out_f32 else 5e-3)
+        if stats:
+            o = out.float().reshape(nb, h * w, cout)
+            ok &= report(name + " [stats sum]", st[:, :, 0], o.sum(1), 1e-3)
+            ok &= report(name + " [stats sumsq]", st[:, :, 1], (o * o).sum(1), 1e-3)
         if split_k > 1:
-            ok &= report(name + " [ws clean]", ws, torch.zeros_like(ws), 0.0)
+            ok &= report(name + " [counters reset]", cnt.float(), torch.zeros_like(cnt).float(), 0.0)
 
     if group == "simple":
         conv_case("simple linear 256x320->320", 1, 1, 256, 320, 320, taps=1, simple=True)
@@ -148,12 +155,44 @@ def run_group(group):
         conv_case("igemm conv3x3 dual-source 1280+640->1280", 1, 16, 16, 1280, 1280, extra_src=640)
         conv_case("igemm conv3x3 dual + 1x1 shortcut", 1, 32, 32, 640, 640, extra_src=320, shortcut=True,
                   residual=False)
+        conv_case("igemm conv3x3 +res +stats 2x32x32", 2, 32, 32, 320, 320, residual=True, stats=True)
+        conv_case("igemm conv3x3 +stats 3x8x8 (tile spans images)", 3, 8, 8, 1280, 640, stats=True)
+        conv_case("igemm linear +stats pdl 1x64x64", 1, 64, 64, 320, 320, taps=1, stats=True, pdl=True)
+        conv_case("simple conv3x3 +stats", 2, 8, 8, 64, 64, stats=True, simple=True)
+    elif group == "gn_fused":
+        # GroupNorm whose statistics come from the producers' epilogues (two sources, plain-GEMM producer)
+        nb, hh, c0, c1 = 2, 16, 640, 320
+        hw = hh * hh
+        xs, outs, sts = [], [], []
+        for c in (c0, c1):
+            x = rnd(nb * hw, c)
+            wt = torch.randn(c, c, device=dev) / c ** 0.5
+            o = torch.empty(nb * hw, c, device=dev, dtype=bf)
+            st = torch.zeros(nb, c, 2, device=dev)
+            p = nat.make_igemm_params([x], [c], 1, 1, nb * hw, [(0, 1)], pk.to_bf16(pk.pack_linear(wt)), c, o, c,
+                                      stats=st, stats_hw=hw)
+            nat.igemm(p)
+            outs.append(o)
+            sts.append(st)
+        C = c0 + c1
+        g = torch.randn(C, device=dev)
+        be = torch.randn(C, device=dev)
+        y = torch.empty(nb * hw, C, device=dev, dtype=bf)
+        nat.groupnorm_apply_cs(outs[0], c0, sts[0], outs[1], c1, sts[1], nb, hw, 32, g, be, 1e-5, True, y)
+        torch.cuda.synchronize()
+        xc = torch.cat([o.float() for o in outs], dim=1).reshape(nb, hw, C).permute(0, 2, 1)
+        ref = F.silu(F.group_norm(xc, 32, g, be, 1e-5)).permute(0, 2, 1).reshape(nb * hw, C)
+        ok &= report("groupnorm from fused producer statistics (2 sources)", y, ref, 1e-2)
     elif group == "igemm_splitk":
         conv_case("igemm conv3x3 1x8x8 1280->1280 split4", 1, 8, 8, 1280, 1280, split_k=4)
         conv_case("igemm conv3x3 1x16x16 1280->1280 split8 +res", 1, 16, 16, 1280, 1280, split_k=8,
                   residual=True)
         conv_case("igemm linear 256x1280->1280 split3 silu", 1, 1, 256, 1280, 1280, taps=1, split_k=3,
                   act=nat.ACT_SILU)
+        conv_case("igemm conv3x3 1x8x8 1280->1280 split14 bn64 +stats", 1, 8, 8, 1280, 1280, split_k=14,
+                  block_n=64, stats=True, rowbias=True)
+        conv_case("igemm linear geglu 256x1280->10240 split2", 1, 1, 256, 1280, 10240, taps=1, split_k=2,
+                  act=nat.ACT_GEGLU)
     elif group == "norm":
         for (nb, hw, c0, c1) in [(1, 4096, 320, 0), (2, 1024, 640, 320), (1, 256, 1280, 640),
                                  (2, 64, 1280, 1280), (1, 65536, 256, 0)]:
