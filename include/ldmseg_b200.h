@@ -82,13 +82,15 @@ typedef struct ldmseg_igemm_params {
   int block_n;                       /* 0 = choose; else 64 / 128 / 160 / 256 */
   int split_k;                       /* 0/1 = none; >1 needs workspace */
   float* workspace;                  /* split-K partial tiles, f32, tiles*split_k*128*block_n elements */
-  int* tile_counters;                /* split-K: int32 per output tile, zero-initialised (self-resetting) */
+  int* tile_counters;                /* split-K: 8192 int32, zero-initialised once (self-resetting) */
   long long workspace_elems;         /* capacity of workspace in f32 elements */
   float* stats;                      /* optional f32 [nb, n, 2]: += per-(image, channel) sum and sum of
                                         squares of the stored (bf16-rounded) output -- GroupNorm statistics
                                         fused into the producer; caller zeroes it; needs h*w % 32 == 0 */
   int stats_hw;                      /* rows per image for `stats` (0 = h*w); lets a plain [M, K] GEMM
                                         (nb=1, h=1, w=M) produce per-image statistics */
+  int weight_tiled;                  /* 1: weight is stored block-tiled [ceil(n/32)][ktot/64][32][64] (each 32x64
+                                        block 4 KB contiguous, zero-padded rows) instead of row-major [n, ktot] */
   int pdl;                           /* 1: launch with programmatic dependent launch (overlap the prologue
                                         with the previous kernel's tail) */
 } ldmseg_igemm_params;
@@ -116,6 +118,8 @@ int ldmseg_groupnorm_apply_cs(const void* src0, int c0, const float* chan_stats0
 /* Launch every kernel of the library with programmatic dependent launch (prologue of kernel i+1
  * overlaps the tail of kernel i); returns the previous setting. */
 int ldmseg_set_pdl(int enable);
+/* Development switch for kernel experiments (0 in production); returns the previous value. */
+int ldmseg_set_debug(int flags);
 /* LayerNorm over the channel dim of each row (tokens or pixels); replaces nn.LayerNorm in
  * BasicTransformerBlock.norm1/norm3 and LayerNorm2d (ldmseg/models/vae.py:309-322). */
 int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma, const float* beta,

@@ -26,7 +26,7 @@ namespace ldm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kIgemmThreads = 192;
+constexpr int kIgemmThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kABytes = BM * BK * 2;  // 16 KB per stage
 
 struct alignas(64) IgemmKParams {
@@ -52,6 +52,8 @@ struct alignas(64) IgemmKParams {
   int* counters;
   float* stats;       // optional per-(image, channel) {sum, sum of squares} of the stored output
   int stats_hw;       // rows per image for the statistics (the producer may be a plain [M, K] GEMM)
+  int w_tiled;        // weights stored as [N/32][K/64][32][64] blocks (4 KB contiguous per block)
+  int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store
 };
 
 template <int BN>
@@ -60,142 +62,251 @@ struct IgemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 160) ? 5 : 4;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStagingBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 32 f32
+  static constexpr int kStagingBytes = 8 * 32 * 64;   // per epilogue warp: 32 rows x 16 f32
+  static constexpr int kStatBytes = 2 * BN * 2 * 4;    // fused GroupNorm statistics: [2 slots][BN][2] f32
   // stages + epilogue staging + barriers (2*stages + 4) * 8 + tmem ptr + split-K flag, + 1024 slack
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kStagingBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+      kStages * kStageBytes + kStagingBytes + kStatBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
 // ---- epilogue ------------------------------------------------------------------------------
-// A warp owns 32 accumulator rows (its TMEM lane quadrant).  tcgen05.ld hands every thread ONE row
-// (32 consecutive f32 columns); storing that directly would touch 32 different lines per
-// instruction.  The chunk is therefore transposed through a 4 KB per-warp staging buffer
-// (XOR-swizzled 16-byte slots, conflict-free both ways): afterwards lane l holds columns
-// 4*(l&7)..+3 of row 4*i + (l>>3), i = 0..7, so 8 lanes cover 128 contiguous bytes of a row and all
-// global accesses (output, residual, split-K partials) are coalesced.
+// Eight epilogue warps (two per TMEM lane quadrant, splitting the tile's 32-column super-chunks
+// between them) so that two warps per SM sub-partition hide each other's latencies.
+// tcgen05.ld hands every thread ONE accumulator row; storing that directly touches 32 different
+// lines per instruction.  Each 16-column half-chunk is therefore transposed through a 2 KB per-warp
+// staging buffer (rotated 16-byte slots, conflict-free both ways): afterwards lane l holds columns
+// 4*(l&3)..+3 of row 8*it + (l>>2), it = 0..3, so 4 lanes cover 64 contiguous bytes of a row and all
+// global accesses (output, residual, split-K partials) move whole sectors.
 enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2 };
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
+__device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// GELU(x) = x/2 (1 + erf(x/sqrt2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
+// bf16 rounding of the stored product); 2 MUFU + ~12 FMA instead of the branchy erff
+__device__ __forceinline__ float fast_gelu(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(1.f + 0.3275911f * z);
+  float poly = 1.061405429f;
+  poly = poly * t - 1.453152027f;
+  poly = poly * t + 1.421413741f;
+  poly = poly * t - 0.284496736f;
+  poly = poly * t + 0.254829592f;
+  const float erf_abs = 1.f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
-template <int BN, int MODE>
-__device__ __forceinline__ void epilogue_warp(const IgemmKParams& p, uint8_t* stg, uint32_t t_row,
-                                              float* ws_tile, int split_idx, int m_base, int n0,
-                                              int lane) {
-  const int jc = lane & 7;    // 16-byte column slot inside the 32-column chunk
-  const int rsub = lane >> 3;  // row within a group of 4
+// Epilogue arguments held in registers (reading them through the parameter block from inside the loops
+// made every access a load the compiler had to repeat after each global store).
+struct EpiArgs {
+  int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw;
+  const float* bias;
+  const float* rowbias;
+  const __nv_bfloat16* residual;
+  void* out;
+  float* stats;
+};
+
+// One warp, one output tile: processes the super-chunks sc = half, half+2, ... (32 columns each, as two
+// 16-column halves).  `sstat` = per-CTA shared accumulators [2 image slots][BN][2] for the fused
+// GroupNorm statistics.
+template <int BN>
+__device__ __forceinline__ void epilogue_warp(const EpiArgs p, int mode, uint32_t stg, float* sstat,
+                                              uint32_t t_row, float* ws_tile, int split_idx, int m_base,
+                                              int n0, int half, int lane) {
+  const int jc = lane & 3;     // 16-byte column slot inside the 16-column half-chunk
+  const int rsub = lane >> 2;   // row within a group of 8
   constexpr int kTileElems = BM * BN;
-#pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
-    if (n0 + c >= p.N) break;
-    if (MODE != EPI_FINAL) {
-      uint32_t r[32];
-      tmem_ld_32x32(t_row + c, r);
-      tmem_wait_ld();
-      float4* rowp = reinterpret_cast<float4*>(stg + lane * 128);
+  const int m_tile0 = m_base & ~(BM - 1);
+  const bool want_stats = p.stats != nullptr && mode != EPI_PARTIAL;
+  // cooperative split-K reduction: the tile's 16 row groups (8 rows each; this warp's quadrant owns
+  // groups 4q..4q+3) are dealt round-robin to the split CTAs; bit `it` of `mine` = reduce group 4q+it
+  uint32_t mine = 0xf;
+  if (mode == EPI_FINAL) {
+    mine = 0;
+    const int q4 = ((m_base >> 5) & 3) * 4;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        rowp[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-      __syncwarp();
-    }
-    const int col = n0 + c + jc * 4;
-    const bool col_ok = col < p.N;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (MODE != EPI_PARTIAL && p.bias != nullptr && col_ok)
-      bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    float4 s_sum = make_float4(0.f, 0.f, 0.f, 0.f), s_sq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = i * 4 + rsub;
-      const int m = m_base + row;
-      const bool ok = col_ok && m < p.M;
-      float4 v;
-      if (MODE == EPI_FINAL) {
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) {
-          const float* src = ws_tile + (m - (m_base & ~(BM - 1))) * BN + c + jc * 4;
-          for (int sidx = 0; sidx < p.split_k; ++sidx)
-            v = f4_add(v, __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(sidx) * kTileElems)));
-        }
-      } else {
-        v = reinterpret_cast<const float4*>(stg + row * 128)[jc ^ (row & 7)];
-      }
-      if (MODE == EPI_PARTIAL) {
-        if (ok)
-          *reinterpret_cast<float4*>(ws_tile + static_cast<size_t>(split_idx) * kTileElems +
-                                     (m - (m_base & ~(BM - 1))) * BN + c + jc * 4) = v;
-        continue;
-      }
-      v = f4_add(v, bias4);
-      if (p.rowbias != nullptr && ok)
-        v = f4_add(v, __ldg(reinterpret_cast<const float4*>(
-                          p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld + col)));
-      if (p.act == LDMSEG_ACT_GEGLU) {
-        // chunk columns are [16 x h | 16 x g]: slots 0..3 hold h, slots 4..7 the matching g
-        float4 g;
-        g.x = __shfl_xor_sync(0xffffffffu, v.x, 4);
-        g.y = __shfl_xor_sync(0xffffffffu, v.y, 4);
-        g.z = __shfl_xor_sync(0xffffffffu, v.z, 4);
-        g.w = __shfl_xor_sync(0xffffffffu, v.w, 4);
-        if (ok && jc < 4) {
-          uint2 u;
-          u.x = pack_bf16x2(v.x * gelu_erf_f(g.x), v.y * gelu_erf_f(g.y));
-          u.y = pack_bf16x2(v.z * gelu_erf_f(g.z), v.w * gelu_erf_f(g.w));
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                    static_cast<size_t>(m) * p.out_ld + ((n0 + c) >> 1) + jc * 4) = u;
-        }
-        continue;
-      }
-      if (p.residual != nullptr && ok) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.residual + static_cast<size_t>(m) * p.res_ld + col));
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-        v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
-      }
-      if (p.act == LDMSEG_ACT_SILU) {
-        v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
-      }
-      if (p.out_f32) {
-        if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = v;
-      } else {
-        uint2 u;
-        u.x = pack_bf16x2(v.x, v.y);
-        u.y = pack_bf16x2(v.z, v.w);
-        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = u;
-        if (p.stats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          v = make_float4(a.x, a.y, b.x, b.y);
-        }
-      }
-      if (p.stats != nullptr && ok) {
-        s_sum = f4_add(s_sum, v);
-        s_sq = f4_add(s_sq, make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
-      }
-    }
-    if (MODE != EPI_PARTIAL && p.stats != nullptr) {
-      // column sums over the warp's 32 rows (all in one image: HW % 32 == 0 is validated on the host)
-#pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        s_sum.x += __shfl_xor_sync(0xffffffffu, s_sum.x, o);
-        s_sum.y += __shfl_xor_sync(0xffffffffu, s_sum.y, o);
-        s_sum.z += __shfl_xor_sync(0xffffffffu, s_sum.z, o);
-        s_sum.w += __shfl_xor_sync(0xffffffffu, s_sum.w, o);
-        s_sq.x += __shfl_xor_sync(0xffffffffu, s_sq.x, o);
-        s_sq.y += __shfl_xor_sync(0xffffffffu, s_sq.y, o);
-        s_sq.z += __shfl_xor_sync(0xffffffffu, s_sq.z, o);
-        s_sq.w += __shfl_xor_sync(0xffffffffu, s_sq.w, o);
-      }
-      if (rsub == 0 && col_ok && m_base < p.M) {
-        float* st = p.stats + (static_cast<size_t>(m_base / p.stats_hw) * p.N + col) * 2;
-        atomicAdd(st + 0, s_sum.x); atomicAdd(st + 1, s_sq.x);
-        atomicAdd(st + 2, s_sum.y); atomicAdd(st + 3, s_sq.y);
-        atomicAdd(st + 4, s_sum.z); atomicAdd(st + 5, s_sq.z);
-        atomicAdd(st + 6, s_sum.w); atomicAdd(st + 7, s_sq.w);
-      }
-    }
-    if (MODE != EPI_FINAL) __syncwarp();
+    for (int it = 0; it < 4; ++it) mine |= (((q4 + it) % p.split_k) == split_idx ? 1u : 0u) << it;
   }
+  const bool warp_one_image = (p.HW & 31) == 0;
+  const int stat_slot = want_stats ? (m_base / p.stats_hw - m_tile0 / p.stats_hw) : 0;
+#pragma unroll 1
+  for (int sc = half; sc * 32 < BN; sc += 2) {
+    if (n0 + sc * 32 >= p.N) break;
+    float4 hv[4];  // GEGLU: the h half of the super-chunk
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int c16 = sc * 32 + hh * 16;
+      const int col = n0 + c16 + jc * 4;
+      const bool col_ok = col < p.N;
+      // ---- early, latency-tolerant loads (overlap the TMEM load + staging round trip)
+      uint2 resv[4];
+      float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode != EPI_PARTIAL) {
+        if (p.bias != nullptr && col_ok) add4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (p.rowbias != nullptr && col_ok && warp_one_image && m_base < p.M)
+          add4 = f4_add(add4, __ldg(reinterpret_cast<const float4*>(
+                                  p.rowbias + static_cast<size_t>(m_base / p.HW) * p.rowbias_ld + col)));
+        if (p.residual != nullptr) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int m = m_base + it * 8 + rsub;
+            resv[it] = make_uint2(0u, 0u);
+            if (col_ok && m < p.M && ((mine >> it) & 1))
+              resv[it] = __ldg(reinterpret_cast<const uint2*>(p.residual + static_cast<size_t>(m) * p.res_ld + col));
+          }
+        }
+      }
+      // ---- accumulator values of this lane's 4 (row, 4-column) slots
+      if (mode != EPI_FINAL) {
+        uint32_t r[16];
+        tmem_ld_32x16(t_row + c16, r);
+        tmem_wait_ld();
+        const uint32_t rowp = stg + lane * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(rowp + (((j + (lane >> 1)) & 3) << 4),
+                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        __syncwarp();
+      }
+      float4 v[4];
+      if (mode == EPI_FINAL) {
+        // sum the split-K partials with many independent loads in flight
+#pragma unroll
+        for (int it = 0; it < 4; ++it) v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s0 = 0; s0 < p.split_k; s0 += 2) {
+          float4 t[4][2];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int m = m_base + it * 8 + rsub;
+            const bool ok = col_ok && m < p.M && ((mine >> it) & 1);
+            const float* src = ws_tile + static_cast<size_t>(m - m_tile0) * BN + c16 + jc * 4;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              t[it][d] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok && s0 + d < p.split_k)
+                t[it][d] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(s0 + d) * kTileElems));
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) v[it] = f4_add(v[it], f4_add(t[it][0], t[it][1]));
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + rsub;
+          v[it] = lds128(stg + row * 64 + (((jc + (row >> 1)) & 3) << 4));
+        }
+        __syncwarp();  // staging may be overwritten by the next half-chunk
+      }
+      // ---- per-slot epilogue
+      float4 s_sum = make_float4(0.f, 0.f, 0.f, 0.f), s_sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int m = m_base + it * 8 + rsub;
+        const bool ok = col_ok && m < p.M && ((mine >> it) & 1);
+        float4 x = v[it];
+        if (mode == EPI_PARTIAL) {
+          if (ok) *reinterpret_cast<float4*>(ws_tile + static_cast<size_t>(split_idx) * kTileElems +
+                                             static_cast<size_t>(m - m_tile0) * BN + c16 + jc * 4) = x;
+          continue;
+        }
+        x = f4_add(x, add4);
+        if (p.rowbias != nullptr && !warp_one_image && ok)
+          x = f4_add(x, __ldg(reinterpret_cast<const float4*>(
+                            p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld + col)));
+        if (p.act == LDMSEG_ACT_GEGLU) {
+          // super-chunk columns are [16 x h | 16 x g]
+          if (hh == 0) {
+            hv[it] = x;
+          } else if (ok) {
+            uint2 u;
+            u.x = pack_bf16x2(hv[it].x * fast_gelu(x.x), hv[it].y * fast_gelu(x.y));
+            u.y = pack_bf16x2(hv[it].z * fast_gelu(x.z), hv[it].w * fast_gelu(x.w));
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld +
+                                      ((n0 + sc * 32) >> 1) + jc * 4) = u;
+          }
+          continue;
+        }
+        if (p.residual != nullptr) {
+          const float2 a = unpack_bf16x2(resv[it].x), b = unpack_bf16x2(resv[it].y);
+          x.x += a.x; x.y += a.y; x.z += b.x; x.w += b.y;
+        }
+        if (p.act == LDMSEG_ACT_SILU) {
+          x.x = fast_silu(x.x); x.y = fast_silu(x.y); x.z = fast_silu(x.z); x.w = fast_silu(x.w);
+        }
+        if (p.out_f32) {
+          if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = x;
+        } else {
+          uint2 u;
+          u.x = pack_bf16x2(x.x, x.y);
+          u.y = pack_bf16x2(x.z, x.w);
+          if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = u;
+          if (want_stats) {  // statistics of what the consumer will read (bf16-rounded)
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+            x = make_float4(a.x, a.y, b.x, b.y);
+          }
+        }
+        if (want_stats && ok) {
+          s_sum = f4_add(s_sum, x);
+          s_sq = f4_add(s_sq, make_float4(x.x * x.x, x.y * x.y, x.z * x.z, x.w * x.w));
+        }
+      }
+      if (want_stats) {
+        // column sums over this warp's rows (lanes with equal jc), then into the CTA's shared accumulators
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+          s_sum.x += __shfl_xor_sync(0xffffffffu, s_sum.x, o);
+          s_sum.y += __shfl_xor_sync(0xffffffffu, s_sum.y, o);
+          s_sum.z += __shfl_xor_sync(0xffffffffu, s_sum.z, o);
+          s_sum.w += __shfl_xor_sync(0xffffffffu, s_sum.w, o);
+          s_sq.x += __shfl_xor_sync(0xffffffffu, s_sq.x, o);
+          s_sq.y += __shfl_xor_sync(0xffffffffu, s_sq.y, o);
+          s_sq.z += __shfl_xor_sync(0xffffffffu, s_sq.z, o);
+          s_sq.w += __shfl_xor_sync(0xffffffffu, s_sq.w, o);
+        }
+        if (rsub == 0 && col_ok) {
+          float* st = sstat + (static_cast<size_t>(stat_slot) * BN + c16 + jc * 4) * 2;
+          atomicAdd(st + 0, s_sum.x); atomicAdd(st + 1, s_sq.x);
+          atomicAdd(st + 2, s_sum.y); atomicAdd(st + 3, s_sq.y);
+          atomicAdd(st + 4, s_sum.z); atomicAdd(st + 5, s_sq.z);
+          atomicAdd(st + 6, s_sum.w); atomicAdd(st + 7, s_sq.w);
+        }
+      }
+    }
+  }
+}
+
+// After every epilogue warp of the CTA has finished a tile: one global atomic per (image slot, column).
+template <int BN>
+__device__ __forceinline__ void flush_stats(const EpiArgs p, float* sstat, int m_tile0, int n0, int et) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const int img0 = m_tile0 / p.stats_hw;
+  for (int idx = et; idx < 2 * BN; idx += kEpiThreads) {
+    const int slot = idx / BN, colr = idx - slot * BN;
+    const float su = sstat[idx * 2], sq = sstat[idx * 2 + 1];
+    if (n0 + colr < p.N && (su != 0.f || sq != 0.f)) {
+      float* g = p.stats + (static_cast<size_t>(img0 + slot) * p.N + n0 + colr) * 2;
+      atomicAdd(g, su);
+      atomicAdd(g + 1, sq);
+    }
+    sstat[idx * 2] = 0.f;
+    sstat[idx * 2 + 1] = 0.f;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 template <int BN>
@@ -210,12 +321,12 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
   uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes);
+  float* sstat = reinterpret_cast<float*>(smem_stg + Cfg::kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes + Cfg::kStatBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  volatile int* is_last_smem = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,7 +340,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -237,6 +348,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < Cfg::kStatBytes / 4; i += kIgemmThreads) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -283,8 +395,12 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           }
           tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
                       cb * BK, x0 + dx, y0 + dy, b0);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK,
-                      n_tile * BN);
+          if (p.w_tiled)
+            tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb,
+                        n_tile * (BN / 32));
+          else
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK,
+                        n_tile * BN);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -342,9 +458,15 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int et = threadIdx.x - 64;  // 0..127
-    uint8_t* stg = smem_stg + q * (32 * 128);
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;    // which super-chunks of the tile this warp takes
+    const int et = threadIdx.x - 64;     // 0..255
+    const uint32_t stg = smem_u32(smem_stg + (warp - 2) * (32 * 64));
+    EpiArgs ea;
+    ea.M = p.M; ea.N = p.N; ea.HW = p.HW; ea.out_ld = p.out_ld; ea.res_ld = p.res_ld;
+    ea.rowbias_ld = p.rowbias_ld; ea.act = p.act; ea.out_f32 = p.out_f32; ea.split_k = p.split_k;
+    ea.stats_hw = p.stats_hw; ea.bias = p.bias; ea.rowbias = p.rowbias; ea.residual = p.residual;
+    ea.out = p.out; ea.stats = p.stats;
     int it = 0;
     for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
       const int tile = wi / p.split_k;
@@ -359,30 +481,48 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (p.split_k <= 1) {
-        epilogue_warp<BN, EPI_DIRECT>(p, stg, t_row, nullptr, 0, m_base, n0, lane);
+        epilogue_warp<BN>(ea, EPI_DIRECT, stg, sstat, t_row, nullptr, 0, m_base, n0, half, lane);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
+        if (ea.stats != nullptr) flush_stats<BN>(ea, sstat, m_tile * BM, n0, et);
       } else {
-        // split-K: every split stores its partial tile (coalesced, no atomics); the CTA that
-        // arrives last sums the partials and applies the epilogue.
+        // split-K: every split stores its partial tile (coalesced, no atomics); once all splits of the
+        // tile have arrived, each split CTA reduces and finishes its share of the tile's rows.
         float* ws_tile = p.workspace + static_cast<size_t>(tile) * p.split_k * (BM * BN);
-        epilogue_warp<BN, EPI_PARTIAL>(p, stg, t_row, ws_tile, split, m_base, n0, lane);
+        if (!(p.debug & 4))
+          epilogue_warp<BN>(ea, EPI_PARTIAL, stg, sstat, t_row, ws_tile, split, m_base, n0, half, lane);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // publish + wait for the peers: the CTA barrier orders every thread's partial stores before
+        // thread 0's release-atomic (release is cumulative); thread 0 then polls with acquire loads
+        // until all splits of this tile have arrived.  Peers are CTAs of the same persistent grid in
+        // the same round, so they are running or about to be scheduled (1 CTA per SM, grid <= #SMs).
+        if (p.debug & 2) continue;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-          const int old = atomicAdd(p.counters + tile, 1);
-          *is_last_smem = (old == p.split_k - 1) ? 1 : 0;
-          if (old == p.split_k - 1) p.counters[tile] = 0;
+          int seen;
+          asm volatile("atom.release.gpu.global.add.s32 %0, [%1], 1;" : "=r"(seen) : "l"(p.counters + tile) : "memory");
+          uint32_t spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
+            if (++spins > (1u << 26)) __trap();
+          } while (seen < p.split_k);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int is_last = *is_last_smem;
-        if (is_last) {
-          __threadfence();
-          epilogue_warp<BN, EPI_FINAL>(p, stg, 0, ws_tile, 0, m_base, n0, lane);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!(p.debug & 1))
+          epilogue_warp<BN>(ea, EPI_FINAL, stg, sstat, 0, ws_tile, split, m_base, n0, half, lane);
+        if (ea.stats != nullptr) flush_stats<BN>(ea, sstat, m_tile * BM, n0, et);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          // the last CTA to finish its share re-arms both counters for the next launch
+          int* done = p.counters + 4096 + tile;
+          int old;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
+          if (old == p.split_k - 1) {
+            p.counters[tile] = 0;
+            *done = 0;
+          }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }
@@ -405,8 +545,14 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
   const int m = static_cast<int>(idx / ncols);
   const int n = static_cast<int>(idx - static_cast<long long>(m) * ncols);
   const int x = m % p.w, y = (m / p.w) % p.h, b = m / HW;
-  const __nv_bfloat16* wrow =
-      reinterpret_cast<const __nv_bfloat16*>(p.weight) + static_cast<size_t>(n) * p.ktot;
+  const __nv_bfloat16* wbase = reinterpret_cast<const __nv_bfloat16*>(p.weight);
+  const int kblocks = p.ktot / 64;
+  auto wat = [&](int k) -> float {
+    const size_t off = p.weight_tiled
+                           ? ((static_cast<size_t>(n >> 5) * kblocks + (k >> 6)) * 32 + (n & 31)) * 64 + (k & 63)
+                           : static_cast<size_t>(n) * p.ktot + k;
+    return __bfloat162float(wbase[off]);
+  };
   float acc = 0.f;
   int koff = 0;
   for (int s = 0; s < p.nseg; ++s) {
@@ -425,7 +571,7 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
         const __nv_bfloat16* arow =
             a + (static_cast<size_t>(b) * HW + static_cast<size_t>(yy) * p.w + xx) * C;
         for (int c = 0; c < C; ++c)
-          acc += __bfloat162float(arow[c]) * __bfloat162float(wrow[koff + c]);
+          acc += __bfloat162float(arow[c]) * wat(koff + c);
       }
       koff += Cpad;
     }
@@ -464,6 +610,7 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
 }
 
 // ------------------------------------------------------------------------------------------
+int g_debug = 0;
 static int validate(const ldmseg_igemm_params* p) {
   LDM_REQUIRE(p != nullptr, "igemm: null params");
   LDM_REQUIRE(p->nsrc >= 1 && p->nsrc <= LDMSEG_MAX_SRC, "igemm: nsrc out of range");
@@ -507,7 +654,7 @@ static int validate(const ldmseg_igemm_params* p) {
   LDM_REQUIRE(p->n % 4 == 0, "igemm: n must be a multiple of 4 (got %d)", p->n);
   if (p->rowbias) LDM_REQUIRE(p->rowbias_ld % 4 == 0, "igemm: rowbias_ld must be a multiple of 4");
   if (p->stats) {
-    LDM_REQUIRE((p->stats_hw > 0 ? p->stats_hw : hw) % 32 == 0, "igemm: fused statistics need rows per image %% 32 == 0");
+    LDM_REQUIRE((p->stats_hw > 0 ? p->stats_hw : hw) % 64 == 0, "igemm: fused statistics need rows per image %% 64 == 0");
     LDM_REQUIRE(p->act != LDMSEG_ACT_GEGLU, "igemm: fused statistics are not defined for GEGLU");
   }
   return 0;
@@ -589,10 +736,20 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   if (bn == 0) bn = choose_block_n(m_tiles, p->n, num_sms());
   LDM_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "igemm: unsupported block_n %d", bn);
   {
+    if (p->weight_tiled) {
+      // [N/32][K/64][32][64]: every 32-row x 64-k block is 4 KB contiguous -> weight streaming reads
+      // whole DRAM pages instead of 128-byte pieces at a K-row stride
+      const uint64_t kblocks = static_cast<uint64_t>(p->ktot) / BK;
+      uint64_t dims[4] = {BK, 32, kblocks, static_cast<uint64_t>((p->n + 31) / 32)};
+      uint64_t strides[3] = {128, 4096, kblocks * 4096};
+      uint32_t box[4] = {BK, 32, 1, static_cast<uint32_t>(bn / 32)};
+      if (int rc = encode_tmap_bf16(&kp.b_map, p->weight, 4, dims, strides, box)) return rc;
+    } else {
     uint64_t dims[2] = {static_cast<uint64_t>(p->ktot), static_cast<uint64_t>(p->n)};
     uint64_t strides[1] = {static_cast<uint64_t>(p->ktot) * 2};
     uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
     if (int rc = encode_tmap_bf16(&kp.b_map, p->weight, 2, dims, strides, box)) return rc;
+    }
   }
   kp.nseg = p->nseg;
   int num_kb = 0;
@@ -627,10 +784,14 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     const long long need = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k * BM * bn;
     LDM_REQUIRE(p->workspace_elems >= need, "igemm: split-K workspace too small (%lld f32 needed, %lld given)",
                 need, static_cast<long long>(p->workspace_elems));
+    LDM_REQUIRE(static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles <= 4096,
+                "igemm: split-K supports at most 4096 output tiles (tile_counters holds 2 x 4096 int32)");
     kp.workspace = p->workspace;
     kp.counters = p->tile_counters;
   }
   kp.stats = p->stats;
+  kp.debug = g_debug;
+  kp.w_tiled = p->weight_tiled;
   kp.stats_hw = p->stats_hw > 0 ? p->stats_hw : HW;
   const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
   const int grid = static_cast<int>(work < num_sms() ? work : num_sms());
@@ -652,4 +813,10 @@ extern "C" int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream) {
   launch_kernel(igemm_simple_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0,
                 reinterpret_cast<cudaStream_t>(stream), *p, M, p->h * p->w);
   return check_launch("igemm_simple_kernel");
+}
+
+extern "C" int ldmseg_set_debug(int flags) {
+  const int old = ldm::g_debug;
+  ldm::g_debug = flags;
+  return old;
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "ldmseg_ddim_step", "ldmseg_sampler_step", "ldmseg_advance_step", "ldmseg_timestep_sinusoid",
     "ldmseg_small_linear", "ldmseg_convt_shuffle_ln", "ldmseg_bilinear2x_to_nchw",
     "ldmseg_bilinear2x_argmax", "ldmseg_select_row", "ldmseg_ddim_step_indexed", "ldmseg_softmax_rows", "ldmseg_nchw_f32_to_nhwc",
-    "ldmseg_groupnorm_apply_cs", "ldmseg_set_pdl",
+    "ldmseg_groupnorm_apply_cs", "ldmseg_set_pdl", "ldmseg_set_debug",
 ]
 
 
@@ -60,6 +60,7 @@ class IgemmParams(C.Structure):
         ("workspace_elems", C.c_longlong),
         ("stats", C.c_void_p),
         ("stats_hw", C.c_int),
+        ("weight_tiled", C.c_int),
         ("pdl", C.c_int),
     ]
 
@@ -110,6 +111,7 @@ def load() -> C.CDLL:
         "ldmseg_select_row": [vp, i32, vp, i32, vp, vp],
         "ldmseg_groupnorm_apply_cs": [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, vp, vp],
         "ldmseg_set_pdl": [i32],
+        "ldmseg_set_debug": [i32],
         "ldmseg_softmax_rows": [vp, i32, i32, f32, vp, vp],
         "ldmseg_ddim_step_indexed": [vp, vp, i64, vp, vp, i32, f32, i32, i32, f32, i32, vp, vp, vp],
     }
@@ -155,7 +157,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       residual: Optional[torch.Tensor] = None, res_ld: int = 0, act: int = ACT_NONE,
                       block_n: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
                       counters: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-                      stats_hw: int = 0, pdl: bool = False) -> IgemmParams:
+                      stats_hw: int = 0, pdl: bool = False, weight_tiled: bool = False) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -171,7 +173,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.weight = weight.data_ptr()
     p.n = n
     p.ktot = ktot
-    assert weight.numel() >= n * ktot, (weight.shape, n, ktot)
+    assert weight.numel() >= (((n + 31) // 32 * 32) if weight_tiled else n) * ktot, (weight.shape, n, ktot)
     p.bias = _ptr(bias)
     p.rowbias = _ptr(rowbias)
     p.rowbias_ld = rowbias_ld
@@ -188,6 +190,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.workspace_elems = workspace.numel() if workspace is not None else 0
     p.stats = _ptr(stats)
     p.stats_hw = stats_hw
+    p.weight_tiled = int(weight_tiled)
     p.pdl = int(pdl)
     return p
 

@@ -89,3 +89,15 @@ def pack_convT2x2(w: torch.Tensor, b: torch.Tensor):
 
 def to_bf16(w: torch.Tensor) -> torch.Tensor:
     return w.to(torch.bfloat16).contiguous()
+
+
+def tile_pack(w2d: torch.Tensor) -> torch.Tensor:
+    """Row-major packed weight [N, Ktot] (Ktot % 64 == 0) -> block-tiled [ceil(N/32), Ktot/64, 32, 64]:
+    every 32-row x 64-k block is 4 KB contiguous, so the weight stream of a tile reads whole DRAM pages
+    (ldmseg_igemm_params.weight_tiled)."""
+    n, k = w2d.shape
+    assert k % 64 == 0
+    npad = (n + 31) // 32 * 32
+    if npad != n:
+        w2d = torch.cat([w2d, torch.zeros(npad - n, k, dtype=w2d.dtype, device=w2d.device)], dim=0)
+    return w2d.reshape(npad // 32, 32, k // 64, 64).permute(0, 2, 1, 3).contiguous()

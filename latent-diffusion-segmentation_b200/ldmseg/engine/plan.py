@@ -35,15 +35,17 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
         splits = [1]
         if allow_split and tiles < sms:
             s = 2
-            while tiles * s <= sms and num_kb // s >= 3 and s <= 24:
+            while tiles * s <= sms and num_kb // s >= 4 and s <= 16:
                 splits.append(s)
                 s += 1
         for s in splits:
             waves = (tiles * s + sms - 1) // sms
             kb = (num_kb + s - 1) // s
-            item = kb * t_kb + 1500 + chunks * 250
+            # measured (tools/bench_split.py, bench_epi.py): ~5 us of launch + prologue + pipeline fill + epilogue
+            # tail per wave, ~5 us more for the split-K publish / wait-for-peers / reduce pass
+            item = kb * t_kb + 9500 + chunks * 120
             if s > 1:
-                item += chunks * 200 + s * chunks * 160 + 600
+                item += 9500 + chunks * 150
             cost = waves * item
             if cost < best_cost - 1e-9:
                 best_cost, best = cost, (bn, s)
@@ -71,7 +73,9 @@ class WeightsBase:
         return t.detach().to(device=self.device, dtype=dtype or t.dtype).contiguous()
 
     def _gemm(self, name, packed_f32, bias, n, **extra):
-        self.L[name] = _Layer(self._dev(packed_f32, torch.bfloat16),
+        extra.setdefault("ktot", packed_f32.shape[1])
+        extra.setdefault("tiled", True)
+        self.L[name] = _Layer(self._dev(pk.tile_pack(packed_f32), torch.bfloat16),
                               None if bias is None else self._dev(bias.float()), n, **extra)
 
     def _norm(self, name, mod):
@@ -138,7 +142,7 @@ class PlanBase:
                                   rowbias=rowbias, rowbias_ld=self.rowbias_ld if rowbias is not None else 0,
                                   residual=residual, res_ld=residual.shape[1] if residual is not None else 0,
                                   act=act, block_n=bn, split_k=split, workspace=self.ws, counters=self.counters,
-                                  pdl=self.pdl)
+                                  pdl=self.pdl, weight_tiled=bool(layer.extra.get("tiled", False)))
         self._keep.append(p)
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])

@@ -18,7 +18,7 @@ def run_case(nb, h, w, cin, n, taps, bn, split, iters=30, residual=False):
     out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
     bias = torch.randn(n, device=dev)
     res = torch.randn(m, n, device=dev).to(torch.bfloat16) if residual else None
-    ws = torch.zeros(8 * 1024 * 1024, device=dev)
+    ws = torch.zeros(24 * 1024 * 1024, device=dev)
     cnt = torch.zeros(8192, device=dev, dtype=torch.int32)
     p = nat.make_igemm_params([x], [cin], nb, h, w, [(0, taps)], wt, n, out, n, bias=bias, residual=res,
                               res_ld=n, block_n=bn, split_k=split, workspace=ws, counters=cnt)

@@ -46,7 +46,7 @@ def run_group(group):
 
     def conv_case(name, nb, h, w, cin, cout, *, taps=9, bias=True, residual=False, rowbias=False,
                   act=nat.ACT_NONE, out_f32=False, block_n=0, split_k=0, simple=False, extra_src=None,
-                  shortcut=False, stats=False, pdl=False):
+                  shortcut=False, stats=False, pdl=False, tiled=False):
         """out = conv(x (+ extra_src concat)) [+ 1x1 shortcut of the raw sources] ..."""
         nonlocal ok
         srcs_c = [cin] + ([extra_src] if extra_src else [])
@@ -72,7 +72,7 @@ def run_group(group):
                 srcs.append(x_)
                 src_cs.append(c_)
                 segs.append((len(srcs) - 1, 1))
-        wb = pk.to_bf16(packed)
+        wb = pk.to_bf16(pk.tile_pack(packed)) if tiled else pk.to_bf16(packed)
         b = torch.randn(cout, device=dev) if bias else None
         rb = torch.randn(nb, cout, device=dev) if rowbias else None
         n_out = cout // 2 if act == nat.ACT_GEGLU else cout
@@ -82,11 +82,12 @@ def run_group(group):
         ws = cnt = None
         if split_k > 1:
             ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev)   # partials are overwritten, never read stale
-            cnt = torch.zeros(4096, device=dev, dtype=torch.int32)
+            cnt = torch.zeros(8192, device=dev, dtype=torch.int32)
         st = torch.zeros(nb, cout, 2, device=dev) if stats else None
         p = nat.make_igemm_params(srcs, src_cs, nb, h, w, segs, wb, cout, out, n_out, bias=b,
                                   rowbias=rb, rowbias_ld=cout, residual=res, res_ld=cout, act=act,
-                                  block_n=block_n, split_k=split_k, workspace=ws, counters=cnt, stats=st, pdl=pdl)
+                                  block_n=block_n, split_k=split_k, workspace=ws, counters=cnt, stats=st, pdl=pdl,
+                                  weight_tiled=tiled)
         nat.igemm(p, simple=simple)
         if split_k > 1:  # second launch: tile counters must have reset themselves
             if st is not None:
@@ -159,6 +160,12 @@ def run_group(group):
         conv_case("igemm conv3x3 +stats 3x8x8 (tile spans images)", 3, 8, 8, 1280, 640, stats=True)
         conv_case("igemm linear +stats pdl 1x64x64", 1, 64, 64, 320, 320, taps=1, stats=True, pdl=True)
         conv_case("simple conv3x3 +stats", 2, 8, 8, 64, 64, stats=True, simple=True)
+        conv_case("simple conv3x3 tiled weights n=40", 1, 8, 8, 64, 40, simple=True, tiled=True)
+        for bn in (64, 128, 160, 256):
+            conv_case(f"igemm conv3x3 tiled weights bn={bn}", 1, 32, 32, 320, 640, block_n=bn, tiled=True, residual=True)
+        conv_case("igemm conv_out tiled n=4 f32", 1, 64, 64, 320, 4, out_f32=True, tiled=True)
+        conv_case("igemm tiled split-K dual + shortcut", 1, 16, 16, 1280, 1280, extra_src=640, shortcut=True, split_k=5,
+                  tiled=True, stats=True)
     elif group == "gn_fused":
         # GroupNorm whose statistics come from the producers' epilogues (two sources, plain-GEMM producer)
         nb, hh, c0, c1 = 2, 16, 640, 320
