@@ -10,9 +10,14 @@
 // (d, head, which, token, image) loads 64-column panels and zero-fills columns >= d, so head
 // dims that are not multiples of 64 (40, 80, 160) need no padding in HBM.
 //
-// CTA = 192 threads, one (image, head, 128-query tile):
-//   warp 0  TMA producer   warp 1  MMA issuer + TMEM allocator   warps 2..5  softmax / correction
-// TMEM: S double-buffered at columns [0,128) and [128,256), O at [256, 256+d).
+// The softmax (one MUFU.EX2 per score) is the bottleneck at these small head dims, not the MMAs, so
+// the CTA is built to keep the MUFU pipe busy: it owns TWO 128-query tiles of one (image, head), each
+// with its own softmax warpgroup; while one warpgroup exponentiates S_j the tensor core computes the
+// other tile's S and P.V (ping-pong), and K/V tiles are loaded once for both.
+//
+// CTA = 320 threads:  warp 0 TMA producer | warp 1 MMA issuer + TMEM allocator |
+//                     warps 2..5 softmax/correction of query tile 0 | warps 6..9 of query tile 1
+// TMEM: S0 at [0,BKV), S1 at [BKV,2BKV), O0 at [2BKV, 2BKV+dk), O1 at [2BKV+dk, 2BKV+2dk)  (<= 448 columns).
 #include "common.h"
 #include <cstring>
 #include "ptx.cuh"
@@ -20,19 +25,19 @@
 
 namespace ldm {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
 
 template <int D>
 struct AttnCfg {
-  static constexpr int BKV = (D <= 80) ? 128 : 64;
+  static constexpr int BKV = (D <= 40) ? 128 : 64;
   static constexpr int kPanels = (D + 63) / 64;
   static constexpr int kDK = (D + 15) / 16 * 16;
-  static constexpr int kQBytes = kPanels * 128 * 128;
-  static constexpr int kKBytes = kPanels * BKV * 128;
-  static constexpr int kPBytes = (BKV / 64) * 128 * 128;
-  static constexpr int kSmemBytes = kQBytes + 2 * 2 * kKBytes + kPBytes + 16 * 8 + 1024;
+  static constexpr int kQBytes = kPanels * 128 * 128;       // one query tile
+  static constexpr int kKBytes = kPanels * BKV * 128;       // one K (or V) tile
+  static constexpr int kPBytes = (BKV / 64) * 128 * 128;    // one P tile
+  static constexpr int kSmemBytes = 2 * kQBytes + 2 * 2 * kKBytes + 2 * kPBytes + 16 * 8 + 1024;
   static constexpr int kTmemCols = 512;
-  static constexpr int kOCol = 256;
+  static constexpr int kOCol = 2 * BKV;   // S0 at [0,BKV), S1 at [BKV,2BKV), then O0, O1 (dk columns each)
 };
 
 struct alignas(64) AttnKParams {
@@ -42,6 +47,12 @@ struct alignas(64) AttnKParams {
   int nb, ntok, heads;
   float scale_log2;  // (1/sqrt(d)) * log2(e)
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int D>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
@@ -53,27 +64,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sm_q = smem;
-  uint8_t* sm_k = sm_q + Cfg::kQBytes;               // [2 stages][K]
+  uint8_t* sm_q = smem;                              // [2 query tiles][Q]
+  uint8_t* sm_k = sm_q + 2 * Cfg::kQBytes;           // [2 stages][K]
   uint8_t* sm_v = sm_k + 2 * Cfg::kKBytes;           // [2 stages][V]
-  uint8_t* sm_p = sm_v + 2 * Cfg::kKBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + Cfg::kPBytes);
+  uint8_t* sm_p = sm_v + 2 * Cfg::kKBytes;           // [2 query tiles][P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 2 * Cfg::kPBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* s_full = bars + 5;    // [2] per query tile
+  uint64_t* p_full = bars + 7;    // [2]
+  uint64_t* pv_done = bars + 9;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int q_tiles = (p.ntok + 127) / 128;
-  const int qt = blockIdx.x % q_tiles;
-  const int head = (blockIdx.x / q_tiles) % p.heads;
-  const int b = blockIdx.x / (q_tiles * p.heads);
-  const int q0 = qt * 128;
+  const int q_blocks = (p.ntok + 255) / 256;
+  const int qb = blockIdx.x % q_blocks;
+  const int head = (blockIdx.x / q_blocks) % p.heads;
+  const int b = blockIdx.x / (q_blocks * p.heads);
+  const int q0 = qb * 256;
   const int T = (p.ntok + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
@@ -84,9 +95,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -101,9 +112,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, Cfg::kQBytes);
-      for (int pn = 0; pn < kPanels; ++pn)
-        tma_load_5d(sm_q + pn * 128 * 128, &p.map_q, q_full, pn * 64, head, 0, q0, b);
+      mbar_expect_tx(q_full, 2 * Cfg::kQBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int pn = 0; pn < kPanels; ++pn)
+          tma_load_5d(sm_q + t * Cfg::kQBytes + pn * 128 * 128, &p.map_q, q_full, pn * 64, head, 0,
+                      q0 + t * 128, b);
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t n = static_cast<uint32_t>(j >> 1);
@@ -122,61 +135,74 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, kDK, 0, 1);
-      auto issue_s = [&](int j) {
+      auto issue_s = [&](int j, int t) {  // S_t = Q_t K_j^T
         const int st = j & 1;
-        const uint32_t d_tmem = tmem_base + (j & 1) * 128;
+        const uint32_t d_tmem = tmem_base + t * BKV;
 #pragma unroll
         for (int ks = 0; ks < kDK / 16; ++ks) {
           const int pn = ks >> 2, kk = ks & 3;
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sm_q + pn * 128 * 128), 16, 1024) + 2 * kk;
+          const uint64_t a =
+              make_smem_desc_sw128(smem_u32(sm_q + t * Cfg::kQBytes + pn * 128 * 128), 16, 1024) + 2 * kk;
           const uint64_t bd =
-              make_smem_desc_sw128(smem_u32(sm_k + st * Cfg::kKBytes + pn * BKV * 128), 16, 1024) +
-              2 * kk;
+              make_smem_desc_sw128(smem_u32(sm_k + st * Cfg::kKBytes + pn * BKV * 128), 16, 1024) + 2 * kk;
           umma_bf16(d_tmem, a, bd, idesc_s, ks > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int j, int t) {  // O_t += P_t V_j
+        const int st = j & 1;
+        const uint32_t o_tmem = tmem_base + Cfg::kOCol + t * kDK;
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const int pn = ks >> 2, kk = ks & 3;
+          const uint64_t a =
+              make_smem_desc_sw128(smem_u32(sm_p + t * Cfg::kPBytes + pn * 128 * 128), 16, 1024) + 2 * kk;
+          // V tile: rows = kv (128 B each), MN(d)-major; 16 kv rows per k-step = 2048 B
+          const uint64_t bd =
+              make_smem_desc_sw128(smem_u32(sm_v + st * Cfg::kKBytes + ks * 2048), BKV * 128, 1024);
+          umma_bf16(o_tmem, a, bd, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
         }
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_s(0);
+      issue_s(0, 0);
       umma_commit(&s_full[0]);
+      issue_s(0, 1);
+      umma_commit(&s_full[1]);
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
-        if (j + 1 < T) {
-          const int ns = (j + 1) & 1;
-          mbar_wait(&kv_full[ns], static_cast<uint32_t>((j + 1) >> 1) & 1);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], static_cast<uint32_t>(j) & 1);
           tc_fence_after();
-          issue_s(j + 1);
-          umma_commit(&s_full[ns]);
+          issue_pv(j, t);
+          umma_commit(&pv_done[t]);
+          if (t == 1) umma_commit(&kv_empty[st]);  // both P.V products of this K/V stage are queued
+          if (j + 1 < T) {
+            if (t == 0) {
+              mbar_wait(&kv_full[(j + 1) & 1], static_cast<uint32_t>((j + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_s(j + 1, t);  // S_t is free: warpgroup t finished reading it before arriving on p_full
+            umma_commit(&s_full[t]);
+          }
         }
-        mbar_wait(p_full, static_cast<uint32_t>(j) & 1);
-        tc_fence_after();
-        const uint32_t o_tmem = tmem_base + Cfg::kOCol;
-#pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          const int pn = ks >> 2, kk = ks & 3;
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sm_p + pn * 128 * 128), 16, 1024) + 2 * kk;
-          // V tile: rows = kv (128 B each), MN(d)-major; 16 kv rows per k-step = 2048 B
-          const uint64_t bd = make_smem_desc_sw128(
-              smem_u32(sm_v + st * Cfg::kKBytes + ks * 2048), BKV * 128, 1024);
-          umma_bf16(o_tmem, a, bd, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(&kv_empty[st]);
-        umma_commit(pv_done);
       }
     }
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- softmax / correction
-    const int q = warp & 3;
+    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    const int q = warp & 3;         // TMEM lane quadrant
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + t * BKV;
+    const uint32_t o_addr = tmem_base + lane_off + Cfg::kOCol + t * kDK;
+    uint8_t* my_p = sm_p + t * Cfg::kPBytes;
+    const float scale = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < T; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&s_full[buf], static_cast<uint32_t>(j >> 1) & 1);
+      mbar_wait(&s_full[t], static_cast<uint32_t>(j) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_off + buf * 128;
       const int kv_valid = min(BKV, p.ntok - j * BKV);  // columns < kv_valid are real tokens
       // pass 1: row maximum
       float mx = -INFINITY;
@@ -185,15 +211,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(s_addr + c, r);
         tmem_wait_ld();
+        if (kv_valid == BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);
-      // P buffer and O are free once PV of the previous tile has completed
+      const float m_new = fmaxf(m_run, mx * scale);
+      const float alpha = ex2_approx(m_run - m_new);
+      // the P buffer and O are free once P.V of the previous tile has completed
       if (j > 0) {
-        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1);
+        mbar_wait(&pv_done[t], static_cast<uint32_t>(j - 1) & 1);
         tc_fence_after();
       }
       // pass 2: p = exp2(s*scale - m), row sum, bf16 P tile into shared memory (K-major, SW128)
@@ -205,12 +236,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         tmem_wait_ld();
         float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
-          pv[i] = (c + i < kv_valid) ? e : 0.f;
-          rowsum += pv[i];
+        for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), scale, -m_new));
+        if (kv_valid != BKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= kv_valid) pv[i] = 0.f;
         }
-        uint8_t* prow = sm_p + (c >> 6) * (128 * 128) + row * 128;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rowsum += pv[i];
+        uint8_t* prow = my_p + (c >> 6) * (128 * 128) + row * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int chunk = ((c & 63) >> 3) + g;  // 16-byte chunk index within the 128-byte row
@@ -226,28 +260,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       m_run = m_new;
       // correction: O *= alpha (skipped warp-uniformly when no row of this warp changed its max)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        const uint32_t o_addr = tmem_base + lane_off + Cfg::kOCol;
 #pragma unroll 1
-        for (int c = 0; c < kDK; c += 8) {
-          uint32_t r[8];
-          tmem_ld_32x8(o_addr + c, r);
+        for (int c = 0; c < kDK; c += 16) {
+          uint32_t r[16];
+          tmem_ld_32x16(o_addr + c, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x8(o_addr + c, r);
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x8(o_addr + c, *reinterpret_cast<uint32_t(*)[8]>(&r[0]));
+          tmem_st_32x8(o_addr + c + 8, *reinterpret_cast<uint32_t(*)[8]>(&r[8]));
         }
         tmem_wait_st();
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[t]);
     }
     // ---------------------------------------------------------------- final normalisation
-    mbar_wait(pv_done, static_cast<uint32_t>(T - 1) & 1);
+    mbar_wait(&pv_done[t], static_cast<uint32_t>(T - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
-    const uint32_t o_addr = tmem_base + lane_off + Cfg::kOCol;
-    const int tok = q0 + row;
+    const int tok = q0 + t * 128 + row;
     __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * p.ntok + tok) * (p.heads * D) + head * D;
 #pragma unroll 1
     for (int c = 0; c < kDK; c += 8) {
@@ -357,7 +390,7 @@ static int launch_attn(const void* qkv, int nb, int ntok, int heads, void* out, 
                                   Cfg::kSmemBytes));
     configured = true;
   }
-  const int grid = nb * heads * ((ntok + 127) / 128);
+  const int grid = nb * heads * ((ntok + 255) / 256);
   launch_kernel(attn_kernel<D>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
   return check_launch("attn_kernel");
 }

@@ -75,6 +75,7 @@ class WeightsBase:
     def _gemm(self, name, packed_f32, bias, n, **extra):
         extra.setdefault("ktot", packed_f32.shape[1])
         extra.setdefault("tiled", True)
+        extra.setdefault("name", name)
         self.L[name] = _Layer(self._dev(pk.tile_pack(packed_f32), torch.bfloat16),
                               None if bias is None else self._dev(bias.float()), n, **extra)
 
@@ -105,6 +106,7 @@ class PlanBase:
         self.W, self.nb = W, nb
         self.device = W.device
         self.ops: List[Callable[[], None]] = []
+        self.tags: List[str] = []            # one per op: "<family>:<rows>:<layer>" (profiling / ablation only)
         self.n_launch = 0
         self._keep: list = []
         self.ws = torch.zeros(16 * 1024 * 1024, device=self.device, dtype=torch.float32)  # split-K partials
@@ -117,15 +119,16 @@ class PlanBase:
         self.rowbias_ld = 0
         self.pdl = USE_PDL
         arena = self.stats_arena
-        self._op(lambda: arena.zero_(), 1)
+        self._op(lambda: arena.zero_(), 1, tag="memset:0:stats_arena")
 
     def _buf(self, rows, c, dtype=torch.bfloat16):
         t = torch.empty(rows, c, device=self.device, dtype=dtype)
         self._keep.append(t)
         return t
 
-    def _op(self, fn, launches=1):
+    def _op(self, fn, launches=1, tag="misc:0:"):
         self.ops.append(fn)
+        self.tags.append(tag)
         self.n_launch += launches
 
     def _gemm(self, layer: _Layer, srcs, src_c, nb, h, w, segs, out, *, rowbias=None, residual=None,
@@ -146,7 +149,7 @@ class PlanBase:
         self._keep.append(p)
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
-        self._op(lambda p=p: nat.igemm(p))
+        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}")
 
     def _stats_for(self, src, c, hw) -> Optional[torch.Tensor]:
         """Channel-statistics slice for a GroupNorm source written by an igemm of this plan (or None)."""
@@ -175,14 +178,15 @@ class PlanBase:
         cs1 = self._stats_for(src1, c1, hw) if src1 is not None else None
         if cs0 is not None and (src1 is None or cs1 is not None):
             self._op(lambda: nat.groupnorm_apply_cs(src0, c0, cs0, src1, c1, cs1, nb, hw, groups, g, b, eps, silu,
-                                                    out))
+                                                    out), tag=f"gn:{nb * hw}:{name}")
             return
         stats = self.gn_stats
-        self._op(lambda: nat.groupnorm(src0, c0, src1, c1, nb, hw, groups, g, b, eps, silu, out, stats), 3)
+        self._op(lambda: nat.groupnorm(src0, c0, src1, c1, nb, hw, groups, g, b, eps, silu, out, stats), 3,
+                 tag=f"gn3:{nb * hw}:{name}")
 
     def _ln(self, name, src, rows, c, out, silu=False):
         g, b, eps = self.W.norms[name]
-        self._op(lambda: nat.layernorm(src, rows, c, g, b, eps, silu, out))
+        self._op(lambda: nat.layernorm(src, rows, c, g, b, eps, silu, out), tag=f"ln:{rows}:{name}")
 
     def _resnet(self, name, x, cx, skip, cskip, h, w=None, rowbias=None):
         """ResnetBlock2D over x (+ virtually concatenated skip); returns the output buffer."""

@@ -178,7 +178,7 @@ class UNetPlan(PlanBase):
         qkv = self._buf(m, 3 * c)
         self._gemm(W.L[name + ".qkv"], [ln], [c], 1, 1, m, [(0, 1)], qkv)
         ao = self._buf(m, c)
-        self._op(lambda: nat.attention(qkv, nb, hw, heads, d, ao))
+        self._op(lambda: nat.attention(qkv, nb, hw, heads, d, ao), tag=f"attn:{m}:{name}")
         t1 = self._buf(m, c)
         self._gemm(W.L[name + ".to_out"], [ao], [c], 1, 1, m, [(0, 1)], t1, residual=t0)
         ln2 = self._buf(m, c)
@@ -208,7 +208,8 @@ class UNetPlan(PlanBase):
                 skips.append((x, c, h))
             if has_down:
                 col = self._buf(nb * (h // 2) * (h // 2), 9 * c)
-                self._op(lambda x=x, h=h, c=c, col=col: nat.im2col_s2(x, nb, h, h, c, 1, col))
+                self._op(lambda x=x, h=h, c=c, col=col: nat.im2col_s2(x, nb, h, h, c, 1, col),
+                         tag=f"im2col:{nb * h * h}:down{i}")
                 h //= 2
                 y = self._buf(nb * h * h, c)
                 self._gemm(W.L[f"down{i}.down"], [col], [9 * c], 1, 1, nb * h * h, [(0, 1)], y)
@@ -227,7 +228,8 @@ class UNetPlan(PlanBase):
                     x = self._transformer(f"up{i}.attn{j}", x, c, h)
             if has_up:
                 up = self._buf(nb * 4 * h * h, c)
-                self._op(lambda x=x, h=h, c=c, up=up: nat.upsample2x(x, nb, h, h, c, up))
+                self._op(lambda x=x, h=h, c=c, up=up: nat.upsample2x(x, nb, h, h, c, up),
+                         tag=f"upsample:{nb * h * h}:up{i}")
                 h *= 2
                 y = self._buf(nb * h * h, c)
                 self._gemm(W.L[f"up{i}.up"], [up], [c], nb, h, h, [(0, 9)], y)
