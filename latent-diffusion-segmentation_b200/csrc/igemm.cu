@@ -53,6 +53,7 @@ struct alignas(64) IgemmKParams {
   float* stats;       // optional per-(image, channel) {sum, sum of squares} of the stored output
   int stats_hw;       // rows per image for the statistics (the producer may be a plain [M, K] GEMM)
   int w_tiled;        // weights stored as [N/32][K/64][32][64] blocks (4 KB contiguous per block)
+  int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
   int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store
 };
 
@@ -60,57 +61,48 @@ template <int BN>
 struct IgemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 160) ? 5 : 4;
+  // the epilogue needs no shared memory: everything but the barriers goes to the operand ring
+  static constexpr int kStages = (BN <= 64) ? 9 : (BN <= 128) ? 7 : (BN <= 160) ? 6 : 4;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStagingBytes = 8 * 32 * 64;   // per epilogue warp: 32 rows x 16 f32
-  static constexpr int kStatBytes = 2 * BN * 2 * 4;    // fused GroupNorm statistics: [2 slots][BN][2] f32
-  // stages + epilogue staging + barriers (2*stages + 4) * 8 + tmem ptr + split-K flag, + 1024 slack
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kStagingBytes + kStatBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+  // stages + barriers (2*stages + 4) * 8 + tmem ptr, + 1024 alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
 // ---- epilogue ------------------------------------------------------------------------------
-// Eight epilogue warps (two per TMEM lane quadrant, splitting the tile's 32-column super-chunks
-// between them) so that two warps per SM sub-partition hide each other's latencies.
-// tcgen05.ld hands every thread ONE accumulator row; storing that directly touches 32 different
-// lines per instruction.  Each 16-column half-chunk is therefore transposed through a 2 KB per-warp
-// staging buffer (rotated 16-byte slots, conflict-free both ways): afterwards lane l holds columns
-// 4*(l&3)..+3 of row 8*it + (l>>2), it = 0..3, so 4 lanes cover 64 contiguous bytes of a row and all
-// global accesses (output, residual, split-K partials) move whole sectors.
+// Thread = accumulator row.  tcgen05.ld (32x32b.x32) hands every thread 32 consecutive columns of ONE
+// output row, and everything downstream keeps that layout:
+//   * bias / per-image (time-embedding) bias: warp-broadcast float4 loads;
+//   * residual and output: 256-bit vector accesses, i.e. every thread reads / writes whole 32-byte
+//     sectors of its own row (no shared-memory transposition, no warp barriers, ~3 instructions per value;
+//     the previous transposing epilogue spent ~16 and did not fit the instruction cache);
+//   * split-K partials: workspace tiles are laid out [8-column group][row][8] so the same thread = row
+//     pattern is perfectly coalesced both when the partial is stored and when it is reduced;
+//   * fused GroupNorm statistics: a 5-step exchange butterfly turns 32 per-row values x 32 lanes into one
+//     column sum per lane (31 shuffles per quantity), then one red.global per (lane, quantity).
+// Eight epilogue warps: two per TMEM lane quadrant, taking alternate 32-column chunks of the tile.
 enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2 };
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 
-__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
-  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // GELU(x) = x/2 (1 + erf(x/sqrt2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
-// bf16 rounding of the stored product); 2 MUFU + ~12 FMA instead of the branchy erff
+// bf16 rounding of the stored product); 2 MUFU + ~10 FMA instead of the branchy erff
 __device__ __forceinline__ float fast_gelu(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(1.f + 0.3275911f * z);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
   float poly = 1.061405429f;
-  poly = poly * t - 1.453152027f;
-  poly = poly * t + 1.421413741f;
-  poly = poly * t - 0.284496736f;
-  poly = poly * t + 0.254829592f;
+  poly = fmaf(poly, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = 1.f - poly * t * __expf(-z * z);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
 }
 
 // Epilogue arguments held in registers (reading them through the parameter block from inside the loops
 // made every access a load the compiler had to repeat after each global store).
 struct EpiArgs {
-  int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw;
+  int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw, vec_ok;
   const float* bias;
   const float* rowbias;
   const __nv_bfloat16* residual;
@@ -118,198 +110,194 @@ struct EpiArgs {
   float* stats;
 };
 
-// One warp, one output tile: processes the super-chunks sc = half, half+2, ... (32 columns each, as two
-// 16-column halves).  `sstat` = per-CTA shared accumulators [2 image slots][BN][2] for the fused
-// GroupNorm statistics.
-template <int BN>
-__device__ __forceinline__ void epilogue_warp(const EpiArgs p, int mode, uint32_t stg, float* sstat,
-                                              uint32_t t_row, float* ws_tile, int split_idx, int m_base,
-                                              int n0, int half, int lane) {
-  const int jc = lane & 3;     // 16-byte column slot inside the 16-column half-chunk
-  const int rsub = lane >> 2;   // row within a group of 8
-  constexpr int kTileElems = BM * BN;
-  const int m_tile0 = m_base & ~(BM - 1);
-  const bool want_stats = p.stats != nullptr && mode != EPI_PARTIAL;
-  // cooperative split-K reduction: the tile's 16 row groups (8 rows each; this warp's quadrant owns
-  // groups 4q..4q+3) are dealt round-robin to the split CTAs; bit `it` of `mine` = reduce group 4q+it
-  uint32_t mine = 0xf;
-  if (mode == EPI_FINAL) {
-    mine = 0;
-    const int q4 = ((m_base >> 5) & 3) * 4;
+// Column sums over the warp's 32 rows: on return lane l holds sum_rows a[l].
+__device__ __forceinline__ float warp_column_sums(float (&a)[32], int lane) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) mine |= (((q4 + it) % p.split_k) == split_idx ? 1u : 0u) << it;
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? a[i] : a[i + w];
+      const float keep = hi ? a[i + w] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
   }
-  const bool warp_one_image = (p.HW & 31) == 0;
-  const int stat_slot = want_stats ? (m_base / p.stats_hw - m_tile0 / p.stats_hw) : 0;
-#pragma unroll 1
-  for (int sc = half; sc * 32 < BN; sc += 2) {
-    if (n0 + sc * 32 >= p.N) break;
-    float4 hv[4];  // GEGLU: the h half of the super-chunk
+  return a[0];
+}
+
+// Finish one 32-column chunk: v[i] = accumulator of (row m, column col0 + i).
+template <bool GEGLU>
+__device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int m, int img, int img_stats,
+                                           int col0, int lane) {
+  const bool row_ok = m < p.M;
+  const bool full = (col0 + 32 <= p.N) && p.vec_ok;
+  if (full) {
+    if (p.bias != nullptr) {
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int c16 = sc * 32 + hh * 16;
-      const int col = n0 + c16 + jc * 4;
-      const bool col_ok = col < p.N;
-      // ---- early, latency-tolerant loads (overlap the TMEM load + staging round trip)
-      uint2 resv[4];
-      float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mode != EPI_PARTIAL) {
-        if (p.bias != nullptr && col_ok) add4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        if (p.rowbias != nullptr && col_ok && warp_one_image && m_base < p.M)
-          add4 = f4_add(add4, __ldg(reinterpret_cast<const float4*>(
-                                  p.rowbias + static_cast<size_t>(m_base / p.HW) * p.rowbias_ld + col)));
-        if (p.residual != nullptr) {
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+      }
+    }
+    if (p.rowbias != nullptr && row_ok) {
+      const float4* rb = reinterpret_cast<const float4*>(p.rowbias + static_cast<size_t>(img) * p.rowbias_ld + col0);
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = m_base + it * 8 + rsub;
-            resv[it] = make_uint2(0u, 0u);
-            if (col_ok && m < p.M && ((mine >> it) & 1))
-              resv[it] = __ldg(reinterpret_cast<const uint2*>(p.residual + static_cast<size_t>(m) * p.res_ld + col));
-          }
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(rb + j);
+        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+      }
+    }
+    if constexpr (GEGLU) {
+      // chunk columns are [16 x h | 16 x g] -> 16 outputs = one 32-byte sector
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = pack_bf16x2(v[2 * i] * fast_gelu(v[16 + 2 * i]), v[2 * i + 1] * fast_gelu(v[17 + 2 * i]));
+      if (row_ok)
+        stg256(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + (col0 >> 1), o);
+      return;
+    } else {
+      if (p.residual != nullptr && row_ok) {
+        const __nv_bfloat16* rp = p.residual + static_cast<size_t>(m) * p.res_ld + col0;
+        uint32_t r0[8], r1[8];
+        ldg256_nc(rp, r0);
+        ldg256_nc(rp + 16, r1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 a = unpack_bf16x2(r0[i]), b = unpack_bf16x2(r1[i]);
+          v[2 * i] += a.x; v[2 * i + 1] += a.y; v[16 + 2 * i] += b.x; v[17 + 2 * i] += b.y;
         }
       }
-      // ---- accumulator values of this lane's 4 (row, 4-column) slots
-      if (mode != EPI_FINAL) {
-        uint32_t r[16];
-        tmem_ld_32x16(t_row + c16, r);
-        tmem_wait_ld();
-        const uint32_t rowp = stg + lane * 64;
+      if (p.act == LDMSEG_ACT_SILU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          sts128(rowp + (((j + (lane >> 1)) & 3) << 4),
-                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-        __syncwarp();
+        for (int i = 0; i < 32; ++i) v[i] = fast_silu(v[i]);
       }
-      float4 v[4];
-      if (mode == EPI_FINAL) {
-        // sum the split-K partials with many independent loads in flight
+      if (p.out_f32) {
+        if (row_ok) {
+          float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-        for (int s0 = 0; s0 < p.split_k; s0 += 2) {
-          float4 t[4][2];
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = m_base + it * 8 + rsub;
-            const bool ok = col_ok && m < p.M && ((mine >> it) & 1);
-            const float* src = ws_tile + static_cast<size_t>(m - m_tile0) * BN + c16 + jc * 4;
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              t[it][d] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok && s0 + d < p.split_k)
-                t[it][d] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(s0 + d) * kTileElems));
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 4; ++it) v[it] = f4_add(v[it], f4_add(t[it][0], t[it][1]));
+          for (int j = 0; j < 4; ++j) stg256(op + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&v[8 * j]));
         }
       } else {
+        uint32_t o0[8], o1[8];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + rsub;
-          v[it] = lds128(stg + row * 64 + (((jc + (row >> 1)) & 3) << 4));
+        for (int i = 0; i < 8; ++i) {
+          o0[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          o1[i] = pack_bf16x2(v[16 + 2 * i], v[17 + 2 * i]);
         }
-        __syncwarp();  // staging may be overwritten by the next half-chunk
-      }
-      // ---- per-slot epilogue
-      float4 s_sum = make_float4(0.f, 0.f, 0.f, 0.f), s_sq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + col0;
+          stg256(op, o0);
+          stg256(op + 16, o1);
+        }
+        if (p.stats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int m = m_base + it * 8 + rsub;
-        const bool ok = col_ok && m < p.M && ((mine >> it) & 1);
-        float4 x = v[it];
-        if (mode == EPI_PARTIAL) {
-          if (ok) *reinterpret_cast<float4*>(ws_tile + static_cast<size_t>(split_idx) * kTileElems +
-                                             static_cast<size_t>(m - m_tile0) * BN + c16 + jc * 4) = x;
-          continue;
-        }
-        x = f4_add(x, add4);
-        if (p.rowbias != nullptr && !warp_one_image && ok)
-          x = f4_add(x, __ldg(reinterpret_cast<const float4*>(
-                            p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld + col)));
-        if (p.act == LDMSEG_ACT_GEGLU) {
-          // super-chunk columns are [16 x h | 16 x g]
-          if (hh == 0) {
-            hv[it] = x;
-          } else if (ok) {
-            uint2 u;
-            u.x = pack_bf16x2(hv[it].x * fast_gelu(x.x), hv[it].y * fast_gelu(x.y));
-            u.y = pack_bf16x2(hv[it].z * fast_gelu(x.z), hv[it].w * fast_gelu(x.w));
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld +
-                                      ((n0 + sc * 32) >> 1) + jc * 4) = u;
-          }
-          continue;
-        }
-        if (p.residual != nullptr) {
-          const float2 a = unpack_bf16x2(resv[it].x), b = unpack_bf16x2(resv[it].y);
-          x.x += a.x; x.y += a.y; x.z += b.x; x.w += b.y;
-        }
-        if (p.act == LDMSEG_ACT_SILU) {
-          x.x = fast_silu(x.x); x.y = fast_silu(x.y); x.z = fast_silu(x.z); x.w = fast_silu(x.w);
-        }
-        if (p.out_f32) {
-          if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = x;
-        } else {
-          uint2 u;
-          u.x = pack_bf16x2(x.x, x.y);
-          u.y = pack_bf16x2(x.z, x.w);
-          if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + col) = u;
-          if (want_stats) {  // statistics of what the consumer will read (bf16-rounded)
-            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-            x = make_float4(a.x, a.y, b.x, b.y);
+          for (int i = 0; i < 8; ++i) {
+            const float2 a = unpack_bf16x2(o0[i]), b = unpack_bf16x2(o1[i]);
+            v[2 * i] = a.x; v[2 * i + 1] = a.y; v[16 + 2 * i] = b.x; v[17 + 2 * i] = b.y;
           }
         }
-        if (want_stats && ok) {
-          s_sum = f4_add(s_sum, x);
-          s_sq = f4_add(s_sq, make_float4(x.x * x.x, x.y * x.y, x.z * x.z, x.w * x.w));
-        }
       }
-      if (want_stats) {
-        // column sums over this warp's rows (lanes with equal jc), then into the CTA's shared accumulators
+    }
+  } else {
+    // generic path: partial chunks (N = 4, 8, ...) or unaligned leading dimensions; never GEGLU (N % 32 == 0).
+    // Rare and tiny: a rolled loop over a local copy keeps it out of the instruction-cache budget.
+    float tmp[32];
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
-          s_sum.x += __shfl_xor_sync(0xffffffffu, s_sum.x, o);
-          s_sum.y += __shfl_xor_sync(0xffffffffu, s_sum.y, o);
-          s_sum.z += __shfl_xor_sync(0xffffffffu, s_sum.z, o);
-          s_sum.w += __shfl_xor_sync(0xffffffffu, s_sum.w, o);
-          s_sq.x += __shfl_xor_sync(0xffffffffu, s_sq.x, o);
-          s_sq.y += __shfl_xor_sync(0xffffffffu, s_sq.y, o);
-          s_sq.z += __shfl_xor_sync(0xffffffffu, s_sq.z, o);
-          s_sq.w += __shfl_xor_sync(0xffffffffu, s_sq.w, o);
-        }
-        if (rsub == 0 && col_ok) {
-          float* st = sstat + (static_cast<size_t>(stat_slot) * BN + c16 + jc * 4) * 2;
-          atomicAdd(st + 0, s_sum.x); atomicAdd(st + 1, s_sq.x);
-          atomicAdd(st + 2, s_sum.y); atomicAdd(st + 3, s_sq.y);
-          atomicAdd(st + 4, s_sum.z); atomicAdd(st + 5, s_sq.z);
-          atomicAdd(st + 6, s_sum.w); atomicAdd(st + 7, s_sq.w);
-        }
+    for (int i = 0; i < 32; ++i) tmp[i] = v[i];
+    const float* rb = p.rowbias != nullptr ? p.rowbias + static_cast<size_t>(img) * p.rowbias_ld : nullptr;
+    const int ncol = row_ok ? min(32, p.N - col0) : 0;
+#pragma unroll 1
+    for (int i = 0; i < ncol; ++i) {
+      const int col = col0 + i;
+      float x = tmp[i];
+      if (p.bias != nullptr) x += __ldg(p.bias + col);
+      if (rb != nullptr) x += __ldg(rb + col);
+      if (p.residual != nullptr) x += __bfloat162float(p.residual[static_cast<size_t>(m) * p.res_ld + col]);
+      if (p.act == LDMSEG_ACT_SILU) x = fast_silu(x);
+      if (p.out_f32) {
+        reinterpret_cast<float*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = x;
+      } else {
+        const __nv_bfloat16 o = __float2bfloat16(x);
+        reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = o;
+        x = __bfloat162float(o);
+      }
+      tmp[i] = x;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = i < ncol ? tmp[i] : 0.f;
+  }
+  if constexpr (!GEGLU) {
+    if (p.stats != nullptr) {
+      float sq[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (!row_ok) v[i] = 0.f;
+        sq[i] = v[i] * v[i];
+      }
+      const float su = warp_column_sums(v, lane);
+      const float sqs = warp_column_sums(sq, lane);
+      // the warp's 32 rows belong to one image (rows per image % 32 == 0, checked on the host)
+      if (col0 + lane < p.N && m - lane < p.M) {
+        float* g = p.stats + (static_cast<size_t>(img_stats) * p.N + col0 + lane) * 2;
+        atomicAdd(g, su);
+        atomicAdd(g + 1, sqs);
       }
     }
   }
 }
 
-// After every epilogue warp of the CTA has finished a tile: one global atomic per (image slot, column).
-template <int BN>
-__device__ __forceinline__ void flush_stats(const EpiArgs p, float* sstat, int m_tile0, int n0, int et) {
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  const int img0 = m_tile0 / p.stats_hw;
-  for (int idx = et; idx < 2 * BN; idx += kEpiThreads) {
-    const int slot = idx / BN, colr = idx - slot * BN;
-    const float su = sstat[idx * 2], sq = sstat[idx * 2 + 1];
-    if (n0 + colr < p.N && (su != 0.f || sq != 0.f)) {
-      float* g = p.stats + (static_cast<size_t>(img0 + slot) * p.N + n0 + colr) * 2;
-      atomicAdd(g, su);
-      atomicAdd(g + 1, sq);
+// One warp, one output tile: processes the 32-column chunks half, half+2, ...
+//   DIRECT : TMEM -> epilogue -> global            PARTIAL: TMEM -> split-K workspace
+//   FINAL  : sum of the workspace partials -> epilogue -> global, for the chunks dealt to this split
+template <int BN, bool GEGLU, int MODE>
+__device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, float* ws_tile, int split_idx,
+                                              int m_base, int n0, int q, int half, int lane) {
+  constexpr int kChunks = BN / 32;
+  constexpr int kTileElems = BM * BN;
+  const int m = m_base + lane;
+  const int row_in_tile = q * 32 + lane;
+  const int img = m / p.HW;                                       // image of this row (per-image bias)
+  const int img_stats = MODE == EPI_PARTIAL ? 0 : m_base / p.stats_hw;  // image of the warp's rows (statistics)
+#pragma unroll 1
+  for (int ch = half; ch < kChunks; ch += 2) {
+    const int col0 = n0 + ch * 32;
+    if (col0 >= p.N) break;
+    float v[32];
+    if constexpr (MODE == EPI_FINAL) {
+      if ((q * kChunks + ch) % p.split_k != split_idx) continue;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      const float* src = ws_tile + (static_cast<size_t>(ch) * 4 * BM + row_in_tile) * 8;
+#pragma unroll 2
+      for (int s = 0; s < p.split_k; ++s) {
+        uint32_t t[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ldg256_cg(src + static_cast<size_t>(s) * kTileElems + g * (BM * 8), t[g]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * g + i] += __uint_as_float(t[g][i]);
+      }
+    } else {
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + ch * 32, r);
+      tmem_wait_ld();
+      if constexpr (MODE == EPI_PARTIAL) {
+        float* dst = ws_tile + static_cast<size_t>(split_idx) * kTileElems +
+                     (static_cast<size_t>(ch) * 4 * BM + row_in_tile) * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) stg256(dst + g * (BM * 8), *reinterpret_cast<uint32_t(*)[8]>(&r[8 * g]));
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     }
-    sstat[idx * 2] = 0.f;
-    sstat[idx * 2 + 1] = 0.f;
+    epi_finish<GEGLU>(p, v, m, img, img_stats, col0, lane);
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-template <int BN>
+template <int BN, bool GEGLU, bool SPLIT>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
   using Cfg = IgemmCfg<BN>;
@@ -320,9 +308,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;
-  float* sstat = reinterpret_cast<float*>(smem_stg + Cfg::kStagingBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes + Cfg::kStatBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -348,7 +334,6 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < Cfg::kStatBytes / 4; i += kIgemmThreads) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -457,16 +442,15 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;    // which super-chunks of the tile this warp takes
+    const int half = (warp - 2) >> 2;    // which 32-column chunks of the tile this warp takes
     const int et = threadIdx.x - 64;     // 0..255
-    const uint32_t stg = smem_u32(smem_stg + (warp - 2) * (32 * 64));
     EpiArgs ea;
     ea.M = p.M; ea.N = p.N; ea.HW = p.HW; ea.out_ld = p.out_ld; ea.res_ld = p.res_ld;
     ea.rowbias_ld = p.rowbias_ld; ea.act = p.act; ea.out_f32 = p.out_f32; ea.split_k = p.split_k;
-    ea.stats_hw = p.stats_hw; ea.bias = p.bias; ea.rowbias = p.rowbias; ea.residual = p.residual;
-    ea.out = p.out; ea.stats = p.stats;
+    ea.stats_hw = p.stats_hw; ea.vec_ok = p.vec_ok; ea.bias = p.bias; ea.rowbias = p.rowbias;
+    ea.residual = p.residual; ea.out = p.out; ea.stats = p.stats;
     int it = 0;
     for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
       const int tile = wi / p.split_k;
@@ -480,17 +464,16 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if (p.split_k <= 1) {
-        epilogue_warp<BN>(ea, EPI_DIRECT, stg, sstat, t_row, nullptr, 0, m_base, n0, half, lane);
+      if constexpr (!SPLIT) {
+        epilogue_warp<BN, GEGLU, EPI_DIRECT>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
-        if (ea.stats != nullptr) flush_stats<BN>(ea, sstat, m_tile * BM, n0, et);
       } else {
         // split-K: every split stores its partial tile (coalesced, no atomics); once all splits of the
-        // tile have arrived, each split CTA reduces and finishes its share of the tile's rows.
+        // tile have arrived, each split CTA reduces and finishes its share of the tile's chunks.
         float* ws_tile = p.workspace + static_cast<size_t>(tile) * p.split_k * (BM * BN);
         if (!(p.debug & 4))
-          epilogue_warp<BN>(ea, EPI_PARTIAL, stg, sstat, t_row, ws_tile, split, m_base, n0, half, lane);
+          epilogue_warp<BN, GEGLU, EPI_PARTIAL>(ea, t_row, ws_tile, split, m_base, n0, q, half, lane);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
         // publish + wait for the peers: the CTA barrier orders every thread's partial stores before
@@ -510,8 +493,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (!(p.debug & 1))
-          epilogue_warp<BN>(ea, EPI_FINAL, stg, sstat, 0, ws_tile, split, m_base, n0, half, lane);
-        if (ea.stats != nullptr) flush_stats<BN>(ea, sstat, m_tile * BM, n0, et);
+          epilogue_warp<BN, GEGLU, EPI_FINAL>(ea, 0, ws_tile, split, m_base, n0, q, half, lane);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
           // the last CTA to finish its share re-arms both counters for the next launch
@@ -654,18 +636,18 @@ static int validate(const ldmseg_igemm_params* p) {
   LDM_REQUIRE(p->n % 4 == 0, "igemm: n must be a multiple of 4 (got %d)", p->n);
   if (p->rowbias) LDM_REQUIRE(p->rowbias_ld % 4 == 0, "igemm: rowbias_ld must be a multiple of 4");
   if (p->stats) {
-    LDM_REQUIRE((p->stats_hw > 0 ? p->stats_hw : hw) % 64 == 0, "igemm: fused statistics need rows per image %% 64 == 0");
+    LDM_REQUIRE((p->stats_hw > 0 ? p->stats_hw : hw) % 32 == 0, "igemm: fused statistics need rows per image %% 32 == 0");
     LDM_REQUIRE(p->act != LDMSEG_ACT_GEGLU, "igemm: fused statistics are not defined for GEGLU");
   }
   return 0;
 }
 
-template <int BN>
-static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
+template <int BN, bool GEGLU, bool SPLIT>
+static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   using Cfg = IgemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, GEGLU, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
@@ -680,12 +662,21 @@ static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, i
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl || g_pdl) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN>, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT>, kp);
   if (e != cudaSuccess) {
     set_error("igemm_kernel launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
   }
   return check_launch("igemm_kernel");
+}
+
+template <int BN>
+static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
+  const bool geglu = kp.act == LDMSEG_ACT_GEGLU, split = kp.split_k > 1;
+  if (geglu) return split ? launch_igemm_v<BN, true, true>(kp, grid, stream, pdl)
+                          : launch_igemm_v<BN, true, false>(kp, grid, stream, pdl);
+  return split ? launch_igemm_v<BN, false, true>(kp, grid, stream, pdl)
+               : launch_igemm_v<BN, false, false>(kp, grid, stream, pdl);
 }
 
 static int choose_block_n(int m_tiles, int n, int sms) {
@@ -792,6 +783,17 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   kp.stats = p->stats;
   kp.debug = g_debug;
   kp.w_tiled = p->weight_tiled;
+  {
+    const size_t esz = kp.out_f32 ? 4 : 2;
+    bool ok = (reinterpret_cast<uintptr_t>(p->out) & 31) == 0 && (static_cast<size_t>(p->out_ld) * esz) % 32 == 0;
+    if (p->residual)
+      ok = ok && (reinterpret_cast<uintptr_t>(p->residual) & 31) == 0 && (static_cast<size_t>(p->res_ld) * 2) % 32 == 0;
+    if (p->bias) ok = ok && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
+    if (p->rowbias) ok = ok && (reinterpret_cast<uintptr_t>(p->rowbias) & 15) == 0 && p->rowbias_ld % 4 == 0;
+    kp.vec_ok = ok ? 1 : 0;
+    if (p->act == LDMSEG_ACT_GEGLU)
+      LDM_REQUIRE(ok, "igemm: GEGLU needs 32-byte aligned out (ld %% 16 == 0) and 16-byte aligned biases");
+  }
   kp.stats_hw = p->stats_hw > 0 ? p->stats_hw : HW;
   const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
   const int grid = static_cast<int>(work < num_sms() ? work : num_sms());

@@ -168,28 +168,35 @@ def run_group(group):
                   tiled=True, stats=True)
     elif group == "gn_fused":
         # GroupNorm whose statistics come from the producers' epilogues (two sources, plain-GEMM producer)
-        nb, hh, c0, c1 = 2, 16, 640, 320
-        hw = hh * hh
-        xs, outs, sts = [], [], []
-        for c in (c0, c1):
-            x = rnd(nb * hw, c)
-            wt = torch.randn(c, c, device=dev) / c ** 0.5
-            o = torch.empty(nb * hw, c, device=dev, dtype=bf)
-            st = torch.zeros(nb, c, 2, device=dev)
-            p = nat.make_igemm_params([x], [c], 1, 1, nb * hw, [(0, 1)], pk.to_bf16(pk.pack_linear(wt)), c, o, c,
-                                      stats=st, stats_hw=hw)
-            nat.igemm(p)
-            outs.append(o)
-            sts.append(st)
-        C = c0 + c1
-        g = torch.randn(C, device=dev)
-        be = torch.randn(C, device=dev)
-        y = torch.empty(nb * hw, C, device=dev, dtype=bf)
-        nat.groupnorm_apply_cs(outs[0], c0, sts[0], outs[1], c1, sts[1], nb, hw, 32, g, be, 1e-5, True, y)
-        torch.cuda.synchronize()
-        xc = torch.cat([o.float() for o in outs], dim=1).reshape(nb, hw, C).permute(0, 2, 1)
-        ref = F.silu(F.group_norm(xc, 32, g, be, 1e-5)).permute(0, 2, 1).reshape(nb * hw, C)
-        ok &= report("groupnorm from fused producer statistics (2 sources)", y, ref, 1e-2)
+        for (nb, hh, c0, c1, silu) in [(2, 16, 640, 320, True), (1, 64, 320, 0, True), (1, 8, 1280, 1280, True),
+                                       (3, 32, 128, 0, False), (2, 8, 1280, 640, True), (1, 32, 640, 640, False),
+                                       (1, 64, 640, 320, True)]:
+            hw = hh * hh
+            outs, sts = [], []
+            for c in (c0, c1):
+                if c == 0:
+                    outs.append(None)
+                    sts.append(None)
+                    continue
+                x = rnd(nb * hw, c)
+                wt = torch.randn(c, c, device=dev) / c ** 0.5
+                o = torch.empty(nb * hw, c, device=dev, dtype=bf)
+                st = torch.zeros(nb, c, 2, device=dev)
+                p = nat.make_igemm_params([x], [c], 1, 1, nb * hw, [(0, 1)], pk.to_bf16(pk.pack_linear(wt)), c, o, c,
+                                          stats=st, stats_hw=hw)
+                nat.igemm(p)
+                outs.append(o)
+                sts.append(st)
+            C = c0 + c1
+            g = torch.randn(C, device=dev)
+            be = torch.randn(C, device=dev)
+            y = torch.empty(nb * hw, C, device=dev, dtype=bf)
+            nat.groupnorm_apply_cs(outs[0], c0, sts[0], outs[1], c1, sts[1], nb, hw, 32, g, be, 1e-5, silu, y)
+            torch.cuda.synchronize()
+            xc = torch.cat([o.float() for o in outs if o is not None], dim=1).reshape(nb, hw, C).permute(0, 2, 1)
+            ref = F.group_norm(xc, 32, g, be, 1e-5)
+            ref = (F.silu(ref) if silu else ref).permute(0, 2, 1).reshape(nb * hw, C)
+            ok &= report(f"groupnorm from fused producer statistics nb={nb} hw={hw} c={c0}+{c1} silu={silu}", y, ref, 1e-2)
     elif group == "igemm_splitk":
         conv_case("igemm conv3x3 1x8x8 1280->1280 split4", 1, 8, 8, 1280, 1280, split_k=4)
         conv_case("igemm conv3x3 1x16x16 1280->1280 split8 +res", 1, 16, 16, 1280, 1280, split_k=8,
