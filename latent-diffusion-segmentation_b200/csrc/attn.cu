@@ -19,6 +19,7 @@
 //                     warps 2..5 softmax/correction of query tile 0 | warps 6..9 of query tile 1
 // TMEM: S0 at [0,BKV), S1 at [BKV,2BKV), O0 at [2BKV, 2BKV+dk), O1 at [2BKV+dk, 2BKV+2dk)  (<= 448 columns).
 #include "common.h"
+#include <cstdlib>
 #include <cstring>
 #include "ptx.cuh"
 #include "../../include/ldmseg_b200.h"
@@ -35,7 +36,10 @@ struct AttnCfg {
   static constexpr int kQBytes = kPanels * 128 * 128;       // one query tile
   static constexpr int kKBytes = kPanels * BKV * 128;       // one K (or V) tile
   static constexpr int kPBytes = (BKV / 64) * 128 * 128;    // one P tile
-  static constexpr int kSmemBytes = 2 * kQBytes + 2 * 2 * kKBytes + 2 * kPBytes + 16 * 8 + 1024;
+  // K/V ring depth: a K/V tile is only reloaded after both P.V products that read it have completed, and the
+  // next S product needs the tile after that one, so two stages expose the whole TMA latency every iteration
+  static constexpr int kKVStages = (D <= 80) ? 4 : 2;
+  static constexpr int kSmemBytes = 2 * kQBytes + kKVStages * 2 * kKBytes + 2 * kPBytes + 24 * 8 + 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kOCol = 2 * BKV;   // S0 at [0,BKV), S1 at [BKV,2BKV), then O0, O1 (dk columns each)
 };
@@ -54,28 +58,84 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int D>
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// packed fp32x2 arithmetic (FFMA2 / FADD2): half the issue slots of the scalar forms
+__device__ __forceinline__ float2 fma2(float2 a, float s, float c) {
+  uint64_t x, y, z, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(y) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(z) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t x, y, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+__device__ __forceinline__ float2 fma2v(float2 a, float2 b, float2 c) {
+  uint64_t x, y, z, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(z) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+// exp2 on the FMA pipe for a share of the scores (the MUFU pipe, 4 lanes per clock per sub-partition, is what
+// bounds the softmax): round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, 25x below the bf16 rounding of P), exponent patched in with one integer add.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = add2(x, magic);
+  const float2 n = add2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = add2(x, make_float2(-n.x, -n.y));
+  float2 q = fma2v(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  q = fma2v(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = fma2v(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23)));
+}
+constexpr float kRescaleLog2 = 8.f;
+
+// PM: share of the exponentials evaluated on the FMA pipe (0 = none, 1 = half, 2 = a quarter)
+template <int D, int PM>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<D>;
   constexpr int BKV = Cfg::BKV;
   constexpr int kPanels = Cfg::kPanels;
   constexpr int kDK = Cfg::kDK;
+  constexpr int KS = Cfg::kKVStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sm_q = smem;                              // [2 query tiles][Q]
   uint8_t* sm_k = sm_q + 2 * Cfg::kQBytes;           // [2 stages][K]
-  uint8_t* sm_v = sm_k + 2 * Cfg::kKBytes;           // [2 stages][V]
-  uint8_t* sm_p = sm_v + 2 * Cfg::kKBytes;           // [2 query tiles][P]
+  uint8_t* sm_v = sm_k + KS * Cfg::kKBytes;          // [stages][V]
+  uint8_t* sm_p = sm_v + KS * Cfg::kKBytes;          // [2 query tiles][P]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 2 * Cfg::kPBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2] per query tile
-  uint64_t* p_full = bars + 7;    // [2]
-  uint64_t* pv_done = bars + 9;   // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* s_full = bars + 1;    // [2] per query tile
+  uint64_t* p_full = bars + 3;    // [2]
+  uint64_t* pv_done = bars + 5;   // [2]
+  uint64_t* s_free = bars + 7;    // [2] S_t has been copied to registers
+  uint64_t* kv_full = bars + 9;   // [stages]
+  uint64_t* kv_empty = bars + 9 + KS;  // [stages]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9 + 2 * KS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,12 +151,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     tma_prefetch_desc(&p.map_q);
     tma_prefetch_desc(&p.map_kv);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < KS; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 128);
     }
     fence_mbar_init();
   }
@@ -108,7 +171,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_sync();  // the prologue above overlapped the previous kernel; inputs are read from here on
+  // Programmatic dependent launch.  Trigger only now that this CTA owns its TMEM columns: a dependent CTA that
+  // became co-resident earlier could otherwise take them and starve this (prerequisite) grid forever.
+  pdl_trigger();
+  pdl_wait();  // the prologue above overlapped the previous kernel; inputs are read from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -118,8 +184,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
           tma_load_5d(sm_q + t * Cfg::kQBytes + pn * 128 * 128, &p.map_q, q_full, pn * 64, head, 0,
                       q0 + t * 128, b);
       for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t n = static_cast<uint32_t>(j >> 1);
+        const int st = j % KS;
+        const uint32_t n = static_cast<uint32_t>(j / KS);
         mbar_wait(&kv_empty[st], (n & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * Cfg::kKBytes);
         for (int pn = 0; pn < kPanels; ++pn) {
@@ -136,7 +202,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, kDK, 0, 1);
       auto issue_s = [&](int j, int t) {  // S_t = Q_t K_j^T
-        const int st = j & 1;
+        const int st = j % KS;
         const uint32_t d_tmem = tmem_base + t * BKV;
 #pragma unroll
         for (int ks = 0; ks < kDK / 16; ++ks) {
@@ -149,7 +215,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         }
       };
       auto issue_pv = [&](int j, int t) {  // O_t += P_t V_j
-        const int st = j & 1;
+        const int st = j % KS;
         const uint32_t o_tmem = tmem_base + Cfg::kOCol + t * kDK;
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
@@ -169,21 +235,32 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       umma_commit(&s_full[0]);
       issue_s(0, 1);
       umma_commit(&s_full[1]);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
+      // Event loop: the two query tiles advance independently.  Issuing in a fixed order (wait S-free of tile 0,
+      // wait P of tile 0, then tile 1, ...) made each softmax warpgroup wait for the other one's exponentials
+      // before its next S product was even issued.
+      int js[2] = {1, 1};   // next S product to issue per query tile (S_0 is already in flight)
+      int jp[2] = {0, 0};   // next P.V product to issue per query tile
+      while (jp[0] < T || jp[1] < T) {
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], static_cast<uint32_t>(j) & 1);
-          tc_fence_after();
-          issue_pv(j, t);
-          umma_commit(&pv_done[t]);
-          if (t == 1) umma_commit(&kv_empty[st]);  // both P.V products of this K/V stage are queued
-          if (j + 1 < T) {
-            if (t == 0) {
-              mbar_wait(&kv_full[(j + 1) & 1], static_cast<uint32_t>((j + 1) >> 1) & 1);
-              tc_fence_after();
-            }
-            issue_s(j + 1, t);  // S_t is free: warpgroup t finished reading it before arriving on p_full
+          // S_t(j): needs the warpgroup to have copied S_t(j-1) to registers, and K tile j in shared memory
+          if (js[t] < T && mbar_test_wait(&s_free[t], static_cast<uint32_t>(js[t] - 1) & 1) &&
+              mbar_test_wait(&kv_full[js[t] % KS], static_cast<uint32_t>(js[t] / KS) & 1)) {
+            tc_fence_after();
+            issue_s(js[t], t);
             umma_commit(&s_full[t]);
+            ++js[t];
+          }
+          // O_t += P_t(j) V_j
+          if (jp[t] < T && mbar_test_wait(&p_full[t], static_cast<uint32_t>(jp[t]) & 1)) {
+            tc_fence_after();
+            const int j = jp[t];
+            issue_pv(j, t);
+            umma_commit(&pv_done[t]);
+            ++jp[t];
+            // K/V stage j&1 can be refilled once both P.V products of tile j are queued (the S products that
+            // read its K half were issued before the P tiles they lead to)
+            if (jp[t ^ 1] > j) umma_commit(&kv_empty[j % KS]);
           }
         }
       }
@@ -197,68 +274,75 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_off + t * BKV;
     const uint32_t o_addr = tmem_base + lane_off + Cfg::kOCol + t * kDK;
-    uint8_t* my_p = sm_p + t * Cfg::kPBytes;
+    const uint32_t my_p_u32 = smem_u32(sm_p + t * Cfg::kPBytes);
     const float scale = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[t], static_cast<uint32_t>(j) & 1);
       tc_fence_after();
-      const int kv_valid = min(BKV, p.ntok - j * BKV);  // columns < kv_valid are real tokens
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(s_addr + c, r);
-        tmem_wait_ld();
-        if (kv_valid == BKV) {
+      // the whole score row goes to registers in one pass; S_t in TMEM is then free for the next product
+      uint32_t sr[BKV];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+      for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(s_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);
+      const int kv_valid = p.ntok - j * BKV;  // columns < kv_valid are real tokens
+      if (kv_valid < BKV) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kv_valid) sr[i] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m_run, mx * scale);
-      const float alpha = ex2_approx(m_run - m_new);
+      // row maximum (3-input max, four independent chains)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BKV; i += 8) {
+        mx0 = max3f(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
+        mx1 = max3f(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
+        mx2 = max3f(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
+        mx3 = max3f(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;
+      // lazy rescaling: the running maximum only moves when the new one exceeds it by more than 2^8, so P
+      // stays <= 256 (exact in bf16's range, fp32 accumulation) and O is corrected a handful of times per row
+      float alpha = 1.f;
+      if (mx > m_run + kRescaleLog2) {
+        alpha = ex2_approx(m_run - mx);
+        m_run = mx;
+      }
+      const float negm = -m_run;
+      // p = exp2(s*scale - m): packed FFMA2, one MUFU each, packed FADD2 row sums, bf16 pairs
+      float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int i = 0; i < BKV; i += 4) {
+        float2 a = fma2(make_float2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), scale, negm);
+        float2 b = fma2(make_float2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), scale, negm);
+        a.x = ex2_approx(a.x); a.y = ex2_approx(a.y);
+        if (PM == 1 || (PM == 2 && ((i >> 2) & 1))) {
+          b = exp2_poly2(b);
+        } else {
+          b.x = ex2_approx(b.x); b.y = ex2_approx(b.y);
+        }
+        rs0 = add2(rs0, a);
+        rs1 = add2(rs1, b);
+        pk[i / 2] = pack_bf16x2(a.x, a.y);
+        pk[i / 2 + 1] = pack_bf16x2(b.x, b.y);
+      }
+      l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
       // the P buffer and O are free once P.V of the previous tile has completed
       if (j > 0) {
         mbar_wait(&pv_done[t], static_cast<uint32_t>(j - 1) & 1);
         tc_fence_after();
       }
-      // pass 2: p = exp2(s*scale - m), row sum, bf16 P tile into shared memory (K-major, SW128)
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(s_addr + c, r);
-        tmem_wait_ld();
-        float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), scale, -m_new));
-        if (kv_valid != BKV) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i >= kv_valid) pv[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rowsum += pv[i];
-        uint8_t* prow = my_p + (c >> 6) * (128 * 128) + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((c & 63) >> 3) + g;  // 16-byte chunk index within the 128-byte row
-          uint4 u;
-          u.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          u.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          u.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          u.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = u;
-        }
+      for (int c8 = 0; c8 < BKV / 8; ++c8) {
+        const uint32_t prow = my_p_u32 + (c8 >> 3) * (128 * 128) + row * 128;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((c8 & 7) ^ (row & 7)) << 4)),
+                     "r"(pk[4 * c8]), "r"(pk[4 * c8 + 1]), "r"(pk[4 * c8 + 2]), "r"(pk[4 * c8 + 3])
+                     : "memory");
       }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
-      // correction: O *= alpha (skipped warp-uniformly when no row of this warp changed its max)
+      // correction: O *= alpha (skipped warp-uniformly when no row of this warp moved its max)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
         for (int c = 0; c < kDK; c += 16) {
@@ -366,8 +450,8 @@ __global__ void attn_simple_kernel(const __nv_bfloat16* __restrict__ qkv, int nb
   }
 }
 
-template <int D>
-static int launch_attn(const void* qkv, int nb, int ntok, int heads, void* out, cudaStream_t st) {
+template <int D, int PM>
+static int launch_attn_pm(const void* qkv, int nb, int ntok, int heads, void* out, cudaStream_t st) {
   using Cfg = AttnCfg<D>;
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -386,13 +470,27 @@ static int launch_attn(const void* qkv, int nb, int ntok, int heads, void* out, 
   kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = nb * heads * ((ntok + 255) / 256);
-  launch_kernel(attn_kernel<D>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
+  launch_kernel(attn_kernel<D, PM>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
   return check_launch("attn_kernel");
+}
+
+template <int D>
+static int launch_attn(const void* qkv, int nb, int ntok, int heads, void* out, cudaStream_t st) {
+  static int pm = -1;
+  if (pm < 0) {
+    const char* e = getenv("LDMSEG_ATTN_POLY");
+    pm = e ? atoi(e) : 2;
+  }
+  switch (pm) {
+    case 0: return launch_attn_pm<D, 0>(qkv, nb, ntok, heads, out, st);
+    case 1: return launch_attn_pm<D, 1>(qkv, nb, ntok, heads, out, st);
+    default: return launch_attn_pm<D, 2>(qkv, nb, ntok, heads, out, st);
+  }
 }
 
 }  // namespace ldm

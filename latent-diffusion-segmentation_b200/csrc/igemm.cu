@@ -340,7 +340,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here
   // on we touch memory it produced.  (No-ops when the launch carries no PDL attribute.)
-  pdl_sync();
+  // Programmatic dependent launch.  Trigger only now that this CTA owns its TMEM columns: a dependent CTA that
+  // became co-resident earlier could otherwise take them and starve this (prerequisite) grid forever.
+  pdl_trigger();
+  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int total_work = num_tiles * p.split_k;

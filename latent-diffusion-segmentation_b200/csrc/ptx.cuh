@@ -64,6 +64,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// Non-blocking poll (try_wait may suspend the thread for a while; an event loop wants an immediate answer).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Spin until the phase with the given parity has completed.  With the watchdog on, a wait that
 // never completes (a protocol bug) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -233,12 +247,21 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 }
 
 // ------------------------------------------------------------------ programmatic dependent launch
-// First statement of every kernel that reads memory written by its stream predecessor.  `wait`
-// blocks until all prerequisite grids have completed and their writes are visible; the trigger lets
-// the NEXT kernel's CTAs be scheduled (they block at their own wait).  Both are no-ops without PDL.
-__device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+// `pdl_trigger` lets the NEXT kernel on the stream be launched (its CTAs are scheduled as resources free up
+// and block at their own `pdl_wait`); `pdl_wait` blocks until all prerequisite grids have COMPLETED and their
+// writes are visible.  Triggering first -- before this kernel has even waited for its own predecessor --
+// pipelines launches two deep, which hides the launch latency of chains of few-microsecond kernels.  It is
+// safe because every kernel waits for its immediate predecessor's completion before touching memory, and
+// completion is transitive along the stream.  Both are no-ops without the PDL launch attribute.
+__device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_sync() {
+  pdl_trigger();
+  pdl_wait();
 }
 
 // ------------------------------------------------------------------ 256-bit global accesses (sm_100+)
