@@ -18,6 +18,7 @@
 //
 // Tile: BLOCK_M = 128 output pixels x BN output channels, BLOCK_K = 64 (one 128-byte swizzle row).
 #include "common.h"
+#include <cstdlib>
 #include <cstring>
 #include "ptx.cuh"
 #include "../../include/ldmseg_b200.h"
@@ -53,6 +54,7 @@ struct alignas(64) IgemmKParams {
   float* stats;       // optional per-(image, channel) {sum, sum of squares} of the stored output
   int stats_hw;       // rows per image for the statistics (the producer may be a plain [M, K] GEMM)
   int w_tiled;        // weights stored as [N/32][K/64][32][64] blocks (4 KB contiguous per block)
+  int prefetch_b;     // issue the first work item's weight loads before the grid-dependency wait
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
   int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store
 };
@@ -343,7 +345,6 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   // Programmatic dependent launch.  Trigger only now that this CTA owns its TMEM columns: a dependent CTA that
   // became co-resident earlier could otherwise take them and starve this (prerequisite) grid forever.
   pdl_trigger();
-  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int total_work = num_tiles * p.split_k;
@@ -351,6 +352,30 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      auto load_b = [&](int stage, int kb, int n_tile) {
+        if (p.w_tiled)
+          tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb, n_tile * (BN / 32));
+        else
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK, n_tile * BN);
+      };
+      // Weights are never written inside the stream, so their loads need not wait for the previous kernel:
+      // the first work item's weight tiles go into the (still empty) ring while the predecessor is still running
+      // (-3 % on the batch-1 forward).  Also pulling the rest of the weight slice into L2 from here was measured
+      // and dropped: at batch 8 many M-tiles share a slice and the redundant prefetches cost more than they hide.
+      int prefetched = 0;
+      if (p.prefetch_b) {
+        const int tile = blockIdx.x / p.split_k;
+        const int split = blockIdx.x - tile * p.split_k;
+        const int n_tile = tile % p.num_n_tiles;
+        const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
+        const int kb_end = static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
+        prefetched = min(kStages, kb_end - kb_begin);
+        for (int i = 0; i < prefetched; ++i) {
+          mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
+          load_b(i, kb_begin + i, n_tile);
+        }
+      }
+      pdl_wait();  // activations (and everything else the predecessor wrote) from here on
       int stage = 0;
       uint32_t phase = 0;
       for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
@@ -374,8 +399,13 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         int tap = rem / p.seg_cblocks[seg];
         int cb = rem - tap * p.seg_cblocks[seg];
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const bool b_done = prefetched > 0;  // this stage's weight tile is already in flight
+          if (b_done) {
+            --prefetched;
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          }
           int dx = 0, dy = 0;
           if (p.seg_taps[seg] == 9) {
             dy = tap / 3 - 1;
@@ -383,12 +413,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           }
           tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
                       cb * BK, x0 + dx, y0 + dy, b0);
-          if (p.w_tiled)
-            tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb,
-                        n_tile * (BN / 32));
-          else
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK,
-                        n_tile * BN);
+          if (!b_done) load_b(stage, kb, n_tile);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -446,6 +471,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
+    pdl_wait();
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;    // which 32-column chunks of the tile this warp takes
     const int et = threadIdx.x - 64;     // 0..255
@@ -786,6 +812,14 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   kp.stats = p->stats;
   kp.debug = g_debug;
   kp.w_tiled = p->weight_tiled;
+  {
+    static int mode = -1;  // LDMSEG_IGEMM_PREFETCH=0 disables (A/B timing)
+    if (mode < 0) {
+      const char* e = getenv("LDMSEG_IGEMM_PREFETCH");
+      mode = e ? atoi(e) : 1;
+    }
+    kp.prefetch_b = mode != 0;
+  }
   {
     const size_t esz = kp.out_f32 ? 4 : 2;
     bool ok = (reinterpret_cast<uintptr_t>(p->out) & 31) == 0 && (static_cast<size_t>(p->out_ld) * esz) % 32 == 0;

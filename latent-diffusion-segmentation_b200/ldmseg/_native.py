@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libldmseg_b200.so")
+# LDMSEG_LIB: development override (A/B-timing two builds inside one GPU session); the default is the in-tree build
+_LIB_PATH = os.environ.get("LDMSEG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libldmseg_b200.so")
 
 MAX_SRC = 3
 MAX_SEG = 4
