@@ -1,9 +1,26 @@
-set -x
-mkdir -p gpurun_out
-timeout 900 python tools/kernel_check.py > gpurun_out/kernel_check_7.log 2>&1; echo "kernel_check rc=$?"; grep -E "FAIL|GROUP" gpurun_out/kernel_check_7.log
-for v in prev new prev new; do
-  if [ $v = prev ]; then export LDMSEG_LIB=$PWD/latent-diffusion-segmentation_b200/lib/prev_libldmseg_b200.so; else unset LDMSEG_LIB; fi
-  timeout 600 python tools/ablate_unet.py --batch 8 > gpurun_out/ablate_b8_$v.log 2>&1
-  timeout 600 python tools/ablate_unet.py --batch 1 > gpurun_out/ablate_b1_$v.log 2>&1
-  echo "== $v"; grep -E "full|family igemm" gpurun_out/ablate_b8_$v.log gpurun_out/ablate_b1_$v.log
+# One GPU round: parity tests, smoke, bench (batch 1 + batch 8), in-graph ablation, ncu launch lists + full captures.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
+TAG=${1:-r01}
+O=gpurun_out/$TAG
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
+timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench_b1.json 2> $O/bench_b1.err; echo "bench rc=$?"; cat $O/bench_b1.json
+timeout 600 python bench.py --steps 3 --warmup 3 --batch 8 --no-cpu-baseline > $O/bench_b8.json 2> $O/bench_b8.err; cat $O/bench_b8.json
+timeout 600 python tools/ablate_unet.py --batch 1 --per-op > $O/ablate_b1.log 2>&1; head -40 $O/ablate_b1.log
+timeout 600 python tools/ablate_unet.py --batch 8 --per-op > $O/ablate_b8.log 2>&1; head -40 $O/ablate_b8.log
+NCU="ncu --profile-from-start off --clock-control none"
+for b in 1 8; do
+  timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_unet_b$b.csv python tools/profile_unet.py --batch $b > /dev/null 2>&1
+  python tools/summarize_launches.py $O/launches_unet_b$b.csv > $O/launches_unet_b$b.txt 2>&1
 done
+for w in encode decode; do
+  timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_$w.csv python tools/profile_unet.py --what $w > /dev/null 2>&1
+  python tools/summarize_launches.py $O/launches_$w.csv > $O/launches_$w.txt 2>&1
+done
+timeout 900 $NCU --set full -k regex:igemm -c 90 -o $O/igemm_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
+timeout 900 $NCU --set full --import-source on -k regex:igemm -c 60 -o $O/igemm_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
+timeout 900 $NCU --set full --import-source on -k "regex:attn|gn_|layernorm" -c 40 -o $O/attn_gn_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
+timeout 900 $NCU --set full -k "regex:attn|gn_|layernorm" -c 40 -o $O/attn_gn_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
+ls -la $O
