@@ -89,10 +89,13 @@ typedef struct ldmseg_igemm_params {
                                         fused into the producer; caller zeroes it; needs h*w % 32 == 0 */
   int stats_hw;                      /* rows per image for `stats` (0 = h*w); lets a plain [M, K] GEMM
                                         (nb=1, h=1, w=M) produce per-image statistics */
-  int weight_tiled;                  /* 1: weight is stored block-tiled [ceil(n/32)][ktot/64][32][64] (each 32x64
-                                        block 4 KB contiguous, zero-padded rows) instead of row-major [n, ktot] */
+  int weight_tiled;                  /* 1: weight is stored block-tiled [ceil(n/16)][ktot/64][16][64] (each 16x64
+                                        block 2 KB contiguous, zero-padded rows) instead of row-major [n, ktot] */
   int pdl;                           /* 1: launch with programmatic dependent launch (overlap the prologue
                                         with the previous kernel's tail) */
+  int pair;                          /* 1: CTA pairs (clusters of 2, tcgen05 cta_group::2): 256 x block_n tiles, each
+                                        CTA stages its 128 rows of A and half of the B tile.  Needs weight_tiled,
+                                        block_n in {128, 160, 256} and M > 128 */
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);

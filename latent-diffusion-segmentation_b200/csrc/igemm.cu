@@ -59,12 +59,17 @@ struct alignas(64) IgemmKParams {
   int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster work as one 256 x BN tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
+// A and HALF of the B tile, so a k-block costs 16 KB + BN * 64 B of shared-memory ingest per SM instead of
+// 16 KB + BN * 128 B -- operand ingest, not the tensor pipe, is what bounds the 1-CTA kernel (plan.py).
+template <int BN, bool PAIR = false>
 struct IgemmCfg {
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the epilogue needs no shared memory: everything but the barriers goes to the operand ring
-  static constexpr int kStages = (BN <= 64) ? 9 : (BN <= 128) ? 7 : (BN <= 160) ? 6 : 4;
+  static constexpr int kStages = PAIR ? ((BN <= 160) ? 8 : 6)
+                                      : (BN <= 64) ? 9 : (BN <= 128) ? 7 : (BN <= 160) ? 6 : 4;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // stages + barriers (2*stages + 4) * 8 + tmem ptr, + 1024 alignment slack
   static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
@@ -299,10 +304,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
   }
 }
 
-template <int BN, bool GEGLU, bool SPLIT>
+template <int BN, bool GEGLU, bool SPLIT, bool PAIR>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, PAIR>;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -318,6 +323,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (the leader) issues the MMAs; its full / tmem_empty barriers count both CTAs
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // CTA or CTA pair
+  const int num_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.a_map[p.seg_src[s]]);
@@ -328,16 +337,22 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiThreads);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiThreads : kEpiThreads);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here
@@ -346,43 +361,60 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   // became co-resident earlier could otherwise take them and starve this (prerequisite) grid forever.
   pdl_trigger();
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // work item = (tile, k-split); PAIR: "tile" is a pair tile (two vertically adjacent 128-row tiles x BN) and each
+  // CTA of the pair owns the 128-row tile 2 * m_pair + rank (a phantom one past the end when num_m_tiles is odd:
+  // its loads are zero-filled by TMA and its rows are masked in the epilogue)
+  const int num_tiles = (PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
   const int total_work = num_tiles * p.split_k;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      // PAIR: the loads of BOTH CTAs complete on the leader's full barrier (shared::cluster address); only the
+      // leader arms it, with the bytes of both.  A peer load may land before the leader has armed the phase: the
+      // transaction count just goes negative until the leader's arrive.expect_tx, the phase cannot complete early.
+      const uint32_t full0 = PAIR ? map_to_cta(&full_bar[0], 0) : 0u;
+      constexpr uint32_t kTxBytes = PAIR ? 2 * Cfg::kStageBytes : Cfg::kStageBytes;
+      auto arm = [&](int stage) {
+        if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], kTxBytes);
+      };
       auto load_b = [&](int stage, int kb, int n_tile) {
-        if (p.w_tiled)
-          tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb, n_tile * (BN / 32));
-        else
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK, n_tile * BN);
+        if constexpr (PAIR) {
+          tma_load_4d_2sm(smem_b + stage * Cfg::kBBytes, &p.b_map, full0 + stage * 8, 0, 0, kb,
+                          n_tile * (BN / 16) + static_cast<int>(rank) * (BN / 32));
+        } else {
+          if (p.w_tiled)
+            tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb, n_tile * (BN / 16));
+          else
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK, n_tile * BN);
+        }
       };
       // Weights are never written inside the stream, so their loads need not wait for the previous kernel:
       // the first work item's weight tiles go into the (still empty) ring while the predecessor is still running
       // (-3 % on the batch-1 forward).  Also pulling the rest of the weight slice into L2 from here was measured
       // and dropped: at batch 8 many M-tiles share a slice and the redundant prefetches cost more than they hide.
       int prefetched = 0;
-      if (p.prefetch_b) {
-        const int tile = blockIdx.x / p.split_k;
-        const int split = blockIdx.x - tile * p.split_k;
+      if (p.prefetch_b && unit < total_work) {
+        const int tile = unit / p.split_k;
+        const int split = unit - tile * p.split_k;
         const int n_tile = tile % p.num_n_tiles;
         const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
         const int kb_end = static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
         prefetched = min(kStages, kb_end - kb_begin);
         for (int i = 0; i < prefetched; ++i) {
-          mbar_expect_tx(&full_bar[i], Cfg::kStageBytes);
+          arm(i);
           load_b(i, kb_begin + i, n_tile);
         }
       }
       pdl_wait();  // activations (and everything else the predecessor wrote) from here on
       int stage = 0;
       uint32_t phase = 0;
-      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
+      for (int wi = unit; wi < total_work; wi += num_units) {
         const int tile = wi / p.split_k;
         const int split = wi - tile * p.split_k;
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m_unit = tile / p.num_n_tiles;
+        const int n_tile = tile - m_unit * p.num_n_tiles;
+        const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
         const int m0 = m_tile * BM;
         const int x0 = m0 % p.W;
         const int y0 = (m0 / p.W) % p.H;
@@ -404,15 +436,19 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
             --prefetched;
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            arm(stage);
           }
           int dx = 0, dy = 0;
           if (p.seg_taps[seg] == 9) {
             dy = tap / 3 - 1;
             dx = tap - (tap / 3) * 3 - 1;
           }
-          tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
-                      cb * BK, x0 + dx, y0 + dy, b0);
+          if constexpr (PAIR)
+            tma_load_4d_2sm(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], full0 + stage * 8, cb * BK,
+                            x0 + dx, y0 + dy, b0);
+          else
+            tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
+                        cb * BK, x0 + dx, y0 + dy, b0);
           if (!b_done) load_b(stage, kb, n_tile);
           if (++stage == kStages) {
             stage = 0;
@@ -431,12 +467,12 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    if ((!PAIR || rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
+      for (int wi = unit; wi < total_work; wi += num_units, ++it) {
         const int tile = wi / p.split_k;
         const int split = wi - tile * p.split_k;
         const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
@@ -457,15 +493,20 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage]);   // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (PAIR) umma_commit_2sm(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
       }
     }
     __syncwarp();
@@ -480,12 +521,19 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     ea.rowbias_ld = p.rowbias_ld; ea.act = p.act; ea.out_f32 = p.out_f32; ea.split_k = p.split_k;
     ea.stats_hw = p.stats_hw; ea.vec_ok = p.vec_ok; ea.bias = p.bias; ea.rowbias = p.rowbias;
     ea.residual = p.residual; ea.out = p.out; ea.stats = p.stats;
+    const uint32_t tmem_empty0 = PAIR ? map_to_cta(&tmem_empty[0], 0) : 0u;   // the leader's barrier
+    auto release_acc = [&](int acc) {
+      if constexpr (PAIR) mbar_arrive_cluster(tmem_empty0 + acc * 8);
+      else mbar_arrive(&tmem_empty[acc]);
+    };
     int it = 0;
-    for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++it) {
-      const int tile = wi / p.split_k;
-      const int split = wi - tile * p.split_k;
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+    for (int wi = unit; wi < total_work; wi += num_units, ++it) {
+      const int unit_tile = wi / p.split_k;
+      const int split = wi - unit_tile * p.split_k;
+      const int m_unit = unit_tile / p.num_n_tiles;
+      const int n_tile = unit_tile - m_unit * p.num_n_tiles;
+      const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
+      const int tile = m_tile * p.num_n_tiles + n_tile;   // 128-row output tile (split-K workspace / counters)
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_base = m_tile * BM + q * 32;
@@ -496,7 +544,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       if constexpr (!SPLIT) {
         epilogue_warp<BN, GEGLU, EPI_DIRECT>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane);
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        release_acc(acc);
       } else {
         // split-K: every split stores its partial tile (coalesced, no atomics); once all splits of the
         // tile have arrived, each split CTA reduces and finishes its share of the tile's chunks.
@@ -504,7 +552,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         if (!(p.debug & 4))
           epilogue_warp<BN, GEGLU, EPI_PARTIAL>(ea, t_row, ws_tile, split, m_base, n0, q, half, lane);
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        release_acc(acc);
         // publish + wait for the peers: the CTA barrier orders every thread's partial stores before
         // thread 0's release-atomic (release is cumulative); thread 0 then polls with acquire loads
         // until all splits of this tile have arrived.  Peers are CTAs of the same persistent grid in
@@ -539,10 +587,12 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer may still signal this CTA's barriers / read its operands
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -560,7 +610,7 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
   const int kblocks = p.ktot / 64;
   auto wat = [&](int k) -> float {
     const size_t off = p.weight_tiled
-                           ? ((static_cast<size_t>(n >> 5) * kblocks + (k >> 6)) * 32 + (n & 31)) * 64 + (k & 63)
+                           ? ((static_cast<size_t>(n >> 4) * kblocks + (k >> 6)) * 16 + (n & 15)) * 64 + (k & 63)
                            : static_cast<size_t>(n) * p.ktot + k;
     return __bfloat162float(wbase[off]);
   };
@@ -671,12 +721,12 @@ static int validate(const ldmseg_igemm_params* p) {
   return 0;
 }
 
-template <int BN, bool GEGLU, bool SPLIT>
+template <int BN, bool GEGLU, bool SPLIT, bool PAIR>
 static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, PAIR>;
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, GEGLU, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, GEGLU, SPLIT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
@@ -686,12 +736,23 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   cfg.blockDim = dim3(kIgemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {   // the two CTAs of a pair must share a TPC: cluster of 2 along x
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl || g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl || g_pdl) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT>, kp);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT, PAIR>, kp);
   if (e != cudaSuccess) {
     set_error("igemm_kernel launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
@@ -699,13 +760,13 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   return check_launch("igemm_kernel");
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   const bool geglu = kp.act == LDMSEG_ACT_GEGLU, split = kp.split_k > 1;
-  if (geglu) return split ? launch_igemm_v<BN, true, true>(kp, grid, stream, pdl)
-                          : launch_igemm_v<BN, true, false>(kp, grid, stream, pdl);
-  return split ? launch_igemm_v<BN, false, true>(kp, grid, stream, pdl)
-               : launch_igemm_v<BN, false, false>(kp, grid, stream, pdl);
+  if (geglu) return split ? launch_igemm_v<BN, true, true, PAIR>(kp, grid, stream, pdl)
+                          : launch_igemm_v<BN, true, false, PAIR>(kp, grid, stream, pdl);
+  return split ? launch_igemm_v<BN, false, true, PAIR>(kp, grid, stream, pdl)
+               : launch_igemm_v<BN, false, false, PAIR>(kp, grid, stream, pdl);
 }
 
 static int choose_block_n(int m_tiles, int n, int sms) {
@@ -755,14 +816,21 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   int bn = p->block_n;
   if (bn == 0) bn = choose_block_n(m_tiles, p->n, num_sms());
   LDM_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "igemm: unsupported block_n %d", bn);
+  const bool pair = p->pair != 0;
+  if (pair) {
+    LDM_REQUIRE(p->weight_tiled, "igemm: pair mode needs block-tiled weights");
+    LDM_REQUIRE(bn == 128 || bn == 160 || bn == 256, "igemm: pair mode supports block_n 128 / 160 / 256 (got %d)", bn);
+    LDM_REQUIRE(m_tiles >= 2, "igemm: pair mode needs at least two 128-row tiles");
+  }
   {
     if (p->weight_tiled) {
-      // [N/32][K/64][32][64]: every 32-row x 64-k block is 4 KB contiguous -> weight streaming reads
-      // whole DRAM pages instead of 128-byte pieces at a K-row stride
+      // [N/16][K/64][16][64]: every 16-row x 64-k block is 2 KB contiguous -> weight streaming reads
+      // whole DRAM pages instead of 128-byte pieces at a K-row stride; a CTA of a pair stages half a tile
+      // (bn / 2 rows: 80 for bn = 160, hence 16-row blocks)
       const uint64_t kblocks = static_cast<uint64_t>(p->ktot) / BK;
-      uint64_t dims[4] = {BK, 32, kblocks, static_cast<uint64_t>((p->n + 31) / 32)};
-      uint64_t strides[3] = {128, 4096, kblocks * 4096};
-      uint32_t box[4] = {BK, 32, 1, static_cast<uint32_t>(bn / 32)};
+      uint64_t dims[4] = {BK, 16, kblocks, static_cast<uint64_t>((p->n + 15) / 16)};
+      uint64_t strides[3] = {128, 2048, kblocks * 2048};
+      uint32_t box[4] = {BK, 16, 1, static_cast<uint32_t>(pair ? bn / 32 : bn / 16)};
       if (int rc = encode_tmap_bf16(&kp.b_map, p->weight, 4, dims, strides, box)) return rc;
     } else {
     uint64_t dims[2] = {static_cast<uint64_t>(p->ktot), static_cast<uint64_t>(p->n)};
@@ -801,10 +869,11 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   if (kp.split_k > 1) {
     LDM_REQUIRE(p->workspace != nullptr && p->tile_counters != nullptr,
                 "igemm: split_k > 1 needs workspace and tile_counters");
-    const long long need = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k * BM * bn;
+    const int ws_m_tiles = pair ? (kp.num_m_tiles + 1) / 2 * 2 : kp.num_m_tiles;   // incl. the phantom tile
+    const long long need = static_cast<long long>(ws_m_tiles) * kp.num_n_tiles * kp.split_k * BM * bn;
     LDM_REQUIRE(p->workspace_elems >= need, "igemm: split-K workspace too small (%lld f32 needed, %lld given)",
                 need, static_cast<long long>(p->workspace_elems));
-    LDM_REQUIRE(static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles <= 4096,
+    LDM_REQUIRE(static_cast<long long>(ws_m_tiles) * kp.num_n_tiles <= 4096,
                 "igemm: split-K supports at most 4096 output tiles (tile_counters holds 2 x 4096 int32)");
     kp.workspace = p->workspace;
     kp.counters = p->tile_counters;
@@ -832,14 +901,25 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
       LDM_REQUIRE(ok, "igemm: GEGLU needs 32-byte aligned out (ld %% 16 == 0) and 16-byte aligned biases");
   }
   kp.stats_hw = p->stats_hw > 0 ? p->stats_hw : HW;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pair) {
+    // one CTA pair per work item, at most one pair per TPC
+    const long long work = static_cast<long long>((kp.num_m_tiles + 1) / 2) * kp.num_n_tiles * kp.split_k;
+    const int pairs = num_sms() / 2;
+    const int grid = 2 * static_cast<int>(work < pairs ? work : pairs);
+    switch (bn) {
+      case 128: return launch_igemm<128, true>(kp, grid, st, p->pdl);
+      case 160: return launch_igemm<160, true>(kp, grid, st, p->pdl);
+      default: return launch_igemm<256, true>(kp, grid, st, p->pdl);
+    }
+  }
   const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
   const int grid = static_cast<int>(work < num_sms() ? work : num_sms());
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 64: return launch_igemm<64>(kp, grid, st, p->pdl);
-    case 128: return launch_igemm<128>(kp, grid, st, p->pdl);
-    case 160: return launch_igemm<160>(kp, grid, st, p->pdl);
-    default: return launch_igemm<256>(kp, grid, st, p->pdl);
+    case 64: return launch_igemm<64, false>(kp, grid, st, p->pdl);
+    case 128: return launch_igemm<128, false>(kp, grid, st, p->pdl);
+    case 160: return launch_igemm<160, false>(kp, grid, st, p->pdl);
+    default: return launch_igemm<256, false>(kp, grid, st, p->pdl);
   }
 }
 

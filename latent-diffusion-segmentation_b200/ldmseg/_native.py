@@ -63,6 +63,7 @@ class IgemmParams(C.Structure):
         ("stats_hw", C.c_int),
         ("weight_tiled", C.c_int),
         ("pdl", C.c_int),
+        ("pair", C.c_int),
     ]
 
 
@@ -158,7 +159,8 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       residual: Optional[torch.Tensor] = None, res_ld: int = 0, act: int = ACT_NONE,
                       block_n: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
                       counters: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-                      stats_hw: int = 0, pdl: bool = False, weight_tiled: bool = False) -> IgemmParams:
+                      stats_hw: int = 0, pdl: bool = False, weight_tiled: bool = False,
+                      pair: bool = False) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -174,7 +176,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.weight = weight.data_ptr()
     p.n = n
     p.ktot = ktot
-    assert weight.numel() >= (((n + 31) // 32 * 32) if weight_tiled else n) * ktot, (weight.shape, n, ktot)
+    assert weight.numel() >= (((n + 15) // 16 * 16) if weight_tiled else n) * ktot, (weight.shape, n, ktot)
     p.bias = _ptr(bias)
     p.rowbias = _ptr(rowbias)
     p.rowbias_ld = rowbias_ld
@@ -193,6 +195,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.stats_hw = stats_hw
     p.weight_tiled = int(weight_tiled)
     p.pdl = int(pdl)
+    p.pair = int(pair)
     return p
 
 

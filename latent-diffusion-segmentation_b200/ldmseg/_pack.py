@@ -11,6 +11,9 @@ from typing import Sequence
 import torch
 
 
+TILE_ROWS = 16
+
+
 def _pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
@@ -92,12 +95,12 @@ def to_bf16(w: torch.Tensor) -> torch.Tensor:
 
 
 def tile_pack(w2d: torch.Tensor) -> torch.Tensor:
-    """Row-major packed weight [N, Ktot] (Ktot % 64 == 0) -> block-tiled [ceil(N/32), Ktot/64, 32, 64]:
-    every 32-row x 64-k block is 4 KB contiguous, so the weight stream of a tile reads whole DRAM pages
-    (ldmseg_igemm_params.weight_tiled)."""
+    """Row-major packed weight [N, Ktot] (Ktot % 64 == 0) -> block-tiled [ceil(N/16), Ktot/64, 16, 64]:
+    every 16-row x 64-k block is 2 KB contiguous, so the weight stream of a tile reads whole DRAM pages
+    (ldmseg_igemm_params.weight_tiled).  16 rows: a CTA of a pair stages HALF a B tile, 80 rows at block_n 160."""
     n, k = w2d.shape
     assert k % 64 == 0
-    npad = (n + 31) // 32 * 32
+    npad = (n + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS
     if npad != n:
         w2d = torch.cat([w2d, torch.zeros(npad - n, k, dtype=w2d.dtype, device=w2d.device)], dim=0)
-    return w2d.reshape(npad // 32, 32, k // 64, 64).permute(0, 2, 1, 3).contiguous()
+    return w2d.reshape(npad // TILE_ROWS, TILE_ROWS, k // 64, 64).permute(0, 2, 1, 3).contiguous()

@@ -17,20 +17,26 @@ SMS = 148
 CYC_PER_TMA_ROW = 2.17
 USE_PDL = os.environ.get("LDMSEG_PDL", "1") != "0"
 FUSE_GN_STATS = os.environ.get("LDMSEG_FUSE_GN_STATS", "1") != "0"
+USE_PAIR = os.environ.get("LDMSEG_PAIR", "1") != "0"     # CTA pairs (tcgen05 cta_group::2) where the model prefers them
 
 
-def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True) -> Tuple[int, int]:
-    """Pick (block_n, split_k) for an igemm of M x N with num_kb 64-wide K blocks.
+def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
+                  allow_pair: bool = False) -> Tuple[int, int, bool]:
+    """Pick (block_n, split_k, pair) for an igemm of M x N with num_kb 64-wide K blocks.
 
-    Cycle model per work item (one CTA, one output tile, one K split):
-        k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + bn))  +  prologue  +  epilogue
-    items run in waves of `sms` CTAs.  Split-K (partials to a workspace, last CTA reduces) is considered
+    Cycle model per work item (one CTA, one 128 x bn output tile, one K split):
+        k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + B rows staged by the CTA))  +  prologue  +  epilogue
+    items run in waves of `sms` CTAs.  A CTA pair (cta_group::2, 256 x bn tile) stages only bn/2 rows of B per CTA;
+    it needs an even number of 128-row tiles.  Split-K (partials to a workspace, cooperative reduce) is considered
     only when the tiles cannot fill the machine, and is charged for the partial store and the reduction."""
     m_tiles = (m + 127) // 128
-    best, best_cost = (128, 1), float("inf")
-    for bn in (256, 160, 128, 64):
+    best, best_cost = (128, 1, False), float("inf")
+    cands = [(bn, False) for bn in (256, 160, 128, 64)]
+    if allow_pair and m_tiles >= 2 and m_tiles % 2 == 0:
+        cands = [(bn, True) for bn in (256, 160, 128)] + cands
+    for bn, pair in cands:
         tiles = m_tiles * ((n + bn - 1) // bn)
-        t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + bn))
+        t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + (bn // 2 if pair else bn)))
         chunks = bn / 32.0
         splits = [1]
         if allow_split and tiles < sms:
@@ -48,7 +54,7 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
                 item += 9500 + chunks * 150
             cost = waves * item
             if cost < best_cost - 1e-9:
-                best_cost, best = cost, (bn, s)
+                best_cost, best = cost, (bn, s, pair)
     return best
 
 
@@ -135,21 +141,22 @@ class PlanBase:
               act=nat.ACT_NONE, out_ld=None, bias="layer", allow_split=True):
         num_kb = sum(taps * ((src_c[s] + 63) // 64) for s, taps in segs)
         m = nb * h * w
-        bn, split = choose_tiling(m, layer.n, num_kb, allow_split=allow_split)
+        tiled = bool(layer.extra.get("tiled", False))
+        bn, split, pair = choose_tiling(m, layer.n, num_kb, allow_split=allow_split, allow_pair=USE_PAIR and tiled)
         tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
         if split > 1 and tiles * split * 128 * bn > self.ws.numel():
-            bn, split = choose_tiling(m, layer.n, num_kb, allow_split=False)
+            bn, split, pair = choose_tiling(m, layer.n, num_kb, allow_split=False, allow_pair=USE_PAIR and tiled)
         p = nat.make_igemm_params(srcs, src_c, nb, h, w, segs, layer.w, layer.n, out,
                                   out_ld if out_ld is not None else out.shape[1],
                                   bias=layer.bias if bias == "layer" else bias,
                                   rowbias=rowbias, rowbias_ld=self.rowbias_ld if rowbias is not None else 0,
                                   residual=residual, res_ld=residual.shape[1] if residual is not None else 0,
                                   act=act, block_n=bn, split_k=split, workspace=self.ws, counters=self.counters,
-                                  pdl=self.pdl, weight_tiled=bool(layer.extra.get("tiled", False)))
+                                  pdl=self.pdl, weight_tiled=tiled, pair=pair)
         self._keep.append(p)
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
-        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}")
+        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}")
 
     def _stats_for(self, src, c, hw) -> Optional[torch.Tensor]:
         """Channel-statistics slice for a GroupNorm source written by an igemm of this plan (or None)."""

@@ -31,7 +31,7 @@ def test_igemm_params_struct_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
     fields = [f[0] for f in nat.IgemmParams._fields_]
-    assert fields == names and len(fields) == 30
+    assert fields == names and len(fields) == 31
 
 
 def test_product_scheduler_host_logic_matches_reference(golden_dir):
@@ -128,9 +128,12 @@ def test_weight_packing_is_a_valid_gemm_layout():
 
 def test_tiling_heuristic():
     from ldmseg.engine.plan import choose_tiling
-    bn, split = choose_tiling(4096, 320, 45)
-    assert bn in (64, 128, 160, 256) and split >= 1
-    bn, split = choose_tiling(64, 1280, 360)          # 8x8 level at batch 1: weight streaming -> split-K
+    bn, split, pair = choose_tiling(4096, 320, 45)
+    assert bn in (64, 128, 160, 256) and split >= 1 and not pair
+    bn, split, pair = choose_tiling(64, 1280, 360, allow_pair=True)   # 8x8 level at batch 1: weight streaming -> split-K
     assert split > 1 and ((64 + 127) // 128) * ((1280 + bn - 1) // bn) * split <= 148
-    bn, split = choose_tiling(8 * 4096, 2560, 5)      # plenty of tiles: no split
+    assert not pair                                   # a single 128-row tile cannot form a CTA pair
+    bn, split, pair = choose_tiling(8 * 4096, 2560, 5)      # plenty of tiles: no split
     assert split == 1
+    bn, split, pair = choose_tiling(8 * 4096, 320, 45, allow_pair=True)   # ingest-bound conv: pair halves the B staging
+    assert pair and bn in (128, 160, 256) and split == 1

@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "gn_fused", "norm", "attn_simple",
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_pair", "gn_fused", "norm", "attn_simple",
           "attn", "elementwise"]
 
 
@@ -46,7 +46,7 @@ def run_group(group):
 
     def conv_case(name, nb, h, w, cin, cout, *, taps=9, bias=True, residual=False, rowbias=False,
                   act=nat.ACT_NONE, out_f32=False, block_n=0, split_k=0, simple=False, extra_src=None,
-                  shortcut=False, stats=False, pdl=False, tiled=False):
+                  shortcut=False, stats=False, pdl=False, tiled=False, pair=False):
         """out = conv(x (+ extra_src concat)) [+ 1x1 shortcut of the raw sources] ..."""
         nonlocal ok
         srcs_c = [cin] + ([extra_src] if extra_src else [])
@@ -72,6 +72,7 @@ def run_group(group):
                 srcs.append(x_)
                 src_cs.append(c_)
                 segs.append((len(srcs) - 1, 1))
+        tiled = tiled or pair
         wb = pk.to_bf16(pk.tile_pack(packed)) if tiled else pk.to_bf16(packed)
         b = torch.randn(cout, device=dev) if bias else None
         rb = torch.randn(nb, cout, device=dev) if rowbias else None
@@ -87,7 +88,7 @@ def run_group(group):
         p = nat.make_igemm_params(srcs, src_cs, nb, h, w, segs, wb, cout, out, n_out, bias=b,
                                   rowbias=rb, rowbias_ld=cout, residual=res, res_ld=cout, act=act,
                                   block_n=block_n, split_k=split_k, workspace=ws, counters=cnt, stats=st, pdl=pdl,
-                                  weight_tiled=tiled)
+                                  weight_tiled=tiled, pair=pair)
         nat.igemm(p, simple=simple)
         if split_k > 1:  # second launch: tile counters must have reset themselves
             if st is not None:
@@ -207,6 +208,29 @@ def run_group(group):
                   block_n=64, stats=True, rowbias=True)
         conv_case("igemm linear geglu 256x1280->10240 split2", 1, 1, 256, 1280, 10240, taps=1, split_k=2,
                   act=nat.ACT_GEGLU)
+    elif group == "igemm_pair":
+        # CTA pairs (cta_group::2): 256 x block_n tiles
+        for bn in (128, 160, 256):
+            conv_case(f"pair linear 4096x320->640 bn={bn}", 1, 1, 4096, 320, 640, taps=1, block_n=bn, pair=True)
+        conv_case("pair conv3x3 1x64x64 320->320 bn160 +res +rowbias +stats", 1, 64, 64, 320, 320, block_n=160,
+                  residual=True, rowbias=True, stats=True, pair=True)
+        conv_case("pair conv3x3 2x32x32 640->640 bn256 pdl", 2, 32, 32, 640, 640, block_n=256, pair=True, pdl=True)
+        conv_case("pair linear 384x640->1280 bn256 (odd tile count)", 1, 1, 384, 640, 1280, taps=1, block_n=256,
+                  pair=True, stats=True)
+        conv_case("pair linear geglu 1024x640->5120 bn256", 1, 1, 1024, 640, 5120, taps=1, act=nat.ACT_GEGLU,
+                  block_n=256, pair=True)
+        conv_case("pair linear 8192x1280->5120 f32 (9 waves)", 1, 1, 8192, 1280, 5120, taps=1, out_f32=True,
+                  block_n=256, pair=True)
+        conv_case("pair conv3x3 8x64x64 320->320 bn160 (4 waves) +stats", 8, 64, 64, 320, 320, block_n=160,
+                  stats=True, pair=True)
+        conv_case("pair conv3x3 dual + 1x1 shortcut bn160", 1, 32, 32, 640, 640, extra_src=320, shortcut=True,
+                  block_n=160, pair=True)
+        conv_case("pair conv3x3 1x16x16 1280->1280 bn256 split4 +res", 1, 16, 16, 1280, 1280, block_n=256,
+                  split_k=4, residual=True, pair=True)
+        conv_case("pair linear 384x1280->1280 bn160 split3 (odd tiles) +stats", 1, 1, 384, 1280, 1280, taps=1,
+                  block_n=160, split_k=3, stats=True, pair=True)
+        conv_case("pair conv3x3 1x64x64 320->4 f32 bn128 (conv_out)", 1, 64, 64, 320, 4, out_f32=True, block_n=128,
+                  pair=True)
     elif group == "norm":
         for (nb, hw, c0, c1) in [(1, 4096, 320, 0), (2, 1024, 640, 320), (1, 256, 1280, 640),
                                  (2, 64, 1280, 1280), (1, 65536, 256, 0)]:
