@@ -374,9 +374,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       // leader arms it, with the bytes of both.  A peer load may land before the leader has armed the phase: the
       // transaction count just goes negative until the leader's arrive.expect_tx, the phase cannot complete early.
       const uint32_t full0 = PAIR ? map_to_cta(&full_bar[0], 0) : 0u;
-      constexpr uint32_t kTxBytes = PAIR ? 2 * Cfg::kStageBytes : Cfg::kStageBytes;
-      auto arm = [&](int stage) {
-        if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], kTxBytes);
+      auto arm = [&](int stage, uint32_t cta_bytes = Cfg::kStageBytes) {
+        if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], PAIR ? 2 * cta_bytes : cta_bytes);
       };
       auto load_b = [&](int stage, int kb, int n_tile) {
         if constexpr (PAIR) {
@@ -432,24 +431,28 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         int cb = rem - tap * p.seg_cblocks[seg];
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const bool b_done = prefetched > 0;  // this stage's weight tile is already in flight
+          // development only (timing experiments, results are garbage): leave an operand's stage contents stale
+          const bool skip_a = (p.debug & 8) && kb > kb_begin, skip_b = (p.debug & 16) && kb > kb_begin;
           if (b_done) {
             --prefetched;
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            arm(stage);
+            arm(stage, (skip_a ? 0 : kABytes) + (skip_b ? 0 : Cfg::kBBytes));
           }
           int dx = 0, dy = 0;
           if (p.seg_taps[seg] == 9) {
             dy = tap / 3 - 1;
             dx = tap - (tap / 3) * 3 - 1;
           }
-          if constexpr (PAIR)
-            tma_load_4d_2sm(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], full0 + stage * 8, cb * BK,
-                            x0 + dx, y0 + dy, b0);
-          else
-            tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
-                        cb * BK, x0 + dx, y0 + dy, b0);
-          if (!b_done) load_b(stage, kb, n_tile);
+          if (!skip_a) {
+            if constexpr (PAIR)
+              tma_load_4d_2sm(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], full0 + stage * 8, cb * BK,
+                              x0 + dx, y0 + dy, b0);
+            else
+              tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
+                          cb * BK, x0 + dx, y0 + dy, b0);
+          }
+          if (!b_done && !skip_b) load_b(stage, kb, n_tile);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -469,6 +472,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     // ------------------------------------------------------------ MMA issuer
     if ((!PAIR || rank == 0) && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
+      // descriptor = constant fields + start address >> 4 (stage s adds s * stage bytes >> 4; never carries out
+      // of the 14-bit field: shared memory is < 256 KB)
+      const uint64_t desc_base = make_smem_desc_sw128(0, 16, 1024);
+      const uint32_t a_lo = (smem_u32(smem_a) & 0x3FFFF) >> 4, b_lo = (smem_u32(smem_b) & 0x3FFFF) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -483,27 +490,54 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        // Two k-blocks per trip: half the barrier polls and address arithmetic per MMA.  (It does not change the
+        // MMA-only rate, measured with the operand loads left out -- tools/bench_ingest.py: 57 % / 65 % / 77 % of
+        // 2 * 4096 MAC/clk at BN 128 / 160 / 256, i.e. a fixed ~58 cycles per M=128, K=16 instruction on top of
+        // 0.42 * BN, also with cta_group::2 -- so wide tiles are what keeps the tensor pipe busy, not the issue loop.)
+        int kb = kb_begin;
+        while (kb < kb_end) {
+          const bool two = kb + 1 < kb_end;
+          const int s0 = stage;
+          const uint32_t ph0 = phase;
+          int s1 = s0 + 1;
+          uint32_t ph1 = ph0;
+          if (s1 == kStages) {
+            s1 = 0;
+            ph1 ^= 1;
+          }
+          const uint64_t ad0 = desc_base + (a_lo + s0 * (kABytes >> 4));
+          const uint64_t bd0 = desc_base + (b_lo + s0 * (Cfg::kBBytes >> 4));
+          const uint64_t ad1 = desc_base + (a_lo + s1 * (kABytes >> 4));
+          const uint64_t bd1 = desc_base + (b_lo + s1 * (Cfg::kBBytes >> 4));
+          mbar_wait(&full_bar[s0], ph0);
+          if (two) mbar_wait(&full_bar[s1], ph1);
           tc_fence_after();
-          const uint64_t adesc =
-              make_smem_desc_sw128(smem_u32(smem_a + stage * kABytes), 16, 1024);
-          const uint64_t bdesc =
-              make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 field
             if constexpr (PAIR)
-              umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             else
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage]);   // frees the stage in both CTAs
-          else umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+          if constexpr (PAIR) umma_commit_2sm(&empty_bar[s0]);   // frees the stage in both CTAs
+          else umma_commit(&empty_bar[s0]);
+          stage = s1;
+          phase = ph1;
+          if (two) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              if constexpr (PAIR) umma_bf16_2sm(d_tmem, ad1 + 2 * k, bd1 + 2 * k, idesc, 1u);
+              else umma_bf16(d_tmem, ad1 + 2 * k, bd1 + 2 * k, idesc, 1u);
+            }
+            if constexpr (PAIR) umma_commit_2sm(&empty_bar[s1]);
+            else umma_commit(&empty_bar[s1]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
+          kb += two ? 2 : 1;
         }
         if constexpr (PAIR) umma_commit_2sm(&tmem_full[acc]);
         else umma_commit(&tmem_full[acc]);
@@ -887,7 +921,7 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
       const char* e = getenv("LDMSEG_IGEMM_PREFETCH");
       mode = e ? atoi(e) : 1;
     }
-    kp.prefetch_b = mode != 0;
+    kp.prefetch_b = mode != 0 && !(g_debug & 24);
   }
   {
     const size_t esz = kp.out_f32 ? 4 : 2;

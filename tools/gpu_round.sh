@@ -1,5 +1,5 @@
-# One GPU round: parity tests, smoke, bench (batch 1 + batch 8), in-graph ablation, ncu launch lists + full captures.
-# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
+# One GPU round: parity tests, smoke, bench (batch 1 + batch 8), in-graph ablation, ncu launch lists + small full captures.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>     (keeps gpurun_out/<tag> well below 64 MiB)
 TAG=${1:-r01}
 O=gpurun_out/$TAG
 mkdir -p $O
@@ -8,19 +8,21 @@ timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "
 timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
 timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench_b1.json 2> $O/bench_b1.err; echo "bench rc=$?"; cat $O/bench_b1.json
 timeout 600 python bench.py --steps 3 --warmup 3 --batch 8 --no-cpu-baseline > $O/bench_b8.json 2> $O/bench_b8.err; cat $O/bench_b8.json
-timeout 600 python tools/ablate_unet.py --batch 1 --per-op > $O/ablate_b1.log 2>&1; head -40 $O/ablate_b1.log
-timeout 600 python tools/ablate_unet.py --batch 8 --per-op > $O/ablate_b8.log 2>&1; head -40 $O/ablate_b8.log
+timeout 300 python tools/ablate_unet.py --batch 1 --per-op > $O/ablate_b1.log 2>&1; head -12 $O/ablate_b1.log
+timeout 300 python tools/ablate_unet.py --batch 8 --per-op > $O/ablate_b8.log 2>&1; head -12 $O/ablate_b8.log
 NCU="ncu --profile-from-start off --clock-control none"
 for b in 1 8; do
-  timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_unet_b$b.csv python tools/profile_unet.py --batch $b > /dev/null 2>&1
+  timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_unet_b$b.csv python tools/profile_unet.py --batch $b > /dev/null 2>&1
   python tools/summarize_launches.py $O/launches_unet_b$b.csv > $O/launches_unet_b$b.txt 2>&1
 done
 for w in encode decode; do
-  timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_$w.csv python tools/profile_unet.py --what $w > /dev/null 2>&1
+  timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_$w.csv python tools/profile_unet.py --what $w > /dev/null 2>&1
   python tools/summarize_launches.py $O/launches_$w.csv > $O/launches_$w.txt 2>&1
 done
-timeout 900 $NCU --set full -k regex:igemm -c 90 -o $O/igemm_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
-timeout 900 $NCU --set full --import-source on -k regex:igemm -c 60 -o $O/igemm_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
-timeout 900 $NCU --set full --import-source on -k "regex:attn|gn_|layernorm" -c 40 -o $O/attn_gn_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
-timeout 900 $NCU --set full -k "regex:attn|gn_|layernorm" -c 40 -o $O/attn_gn_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
-ls -la $O
+# full captures: a window of the forward that holds 64x64-level convs, a transformer block and its attention
+timeout 400 $NCU --set full --import-source on -k regex:igemm -s 2 -c 14 -o $O/igemm_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
+timeout 400 $NCU --set full -k regex:igemm -s 2 -c 14 -o $O/igemm_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
+timeout 400 $NCU --set full -k "regex:attn|gn_|layernorm" -c 10 -o $O/attn_gn_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
+timeout 400 $NCU --set full -k "regex:attn|gn_|layernorm" -c 10 -o $O/attn_gn_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
+for f in igemm_full_b8 igemm_full_b1 attn_gn_full_b8 attn_gn_full_b1; do python tools/ncu_summary.py $O/$f.ncu-rep > $O/$f.txt 2>&1; done
+du -sh $O; ls -la $O
