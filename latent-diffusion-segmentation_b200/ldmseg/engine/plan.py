@@ -25,9 +25,9 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
     """Pick (block_n, split_k, pair) for an igemm of M x N with num_kb 64-wide K blocks.
 
     Cycle model per work item (one CTA, one 128 x bn output tile, one K split):
-        k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + B rows staged by the CTA))  +  prologue  +  epilogue
-    items run in waves of `sms` CTAs.  A CTA pair (cta_group::2, 256 x bn tile) stages only bn/2 rows of B per CTA;
-    it needs an even number of 128-row tiles.  Split-K (partials to a workspace, cooperative reduce) is considered
+        k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + bn))  +  prologue  +  epilogue
+    items run in waves of `sms` CTAs.  A CTA pair (cta_group::2, 256 x bn tile) stages only bn/2 rows of B per CTA
+    (a measured per-k-block saving, against a fixed cluster-launch cost); it needs an even number of 128-row tiles.  Split-K (partials to a workspace, cooperative reduce) is considered
     only when the tiles cannot fill the machine, and is charged for the partial store and the reduction."""
     m_tiles = (m + 127) // 128
     best, best_cost = (128, 1, False), float("inf")
@@ -36,7 +36,13 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
         cands = [(bn, True) for bn in (256, 160, 128)] + cands
     for bn, pair in cands:
         tiles = m_tiles * ((n + bn - 1) // bn)
-        t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + (bn // 2 if pair else bn)))
+        t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + bn))
+        if pair:
+            # measured (tools/bench_ingest.py, in-graph A/B): halving the B staging saves ~45 cycles per k-block at
+            # bn = 160 (the MMA rate of narrow tiles, not ingest, is the larger term), and a cluster launch costs
+            # ~1.5 us more -- pairs win once a CTA runs a few hundred k-blocks (batch 8: -3 % on the forward) and
+            # lose in the single-wave launches of batch 1
+            t_kb -= 45.0 * bn / 160.0
         chunks = bn / 32.0
         splits = [1]
         if allow_split and tiles < sms:
@@ -52,7 +58,7 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
             item = kb * t_kb + 9500 + chunks * 120
             if s > 1:
                 item += 9500 + chunks * 150
-            cost = waves * item
+            cost = waves * item + (3000 if pair else 0)
             if cost < best_cost - 1e-9:
                 best_cost, best = cost, (bn, s, pair)
     return best

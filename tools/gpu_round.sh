@@ -24,5 +24,8 @@ timeout 400 $NCU --set full --import-source on -k regex:igemm -s 2 -c 14 -o $O/i
 timeout 400 $NCU --set full -k regex:igemm -s 2 -c 14 -o $O/igemm_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
 timeout 400 $NCU --set full -k "regex:attn|gn_|layernorm" -c 10 -o $O/attn_gn_full_b8 -f python tools/profile_unet.py --batch 8 > /dev/null 2>&1
 timeout 400 $NCU --set full -k "regex:attn|gn_|layernorm" -c 10 -o $O/attn_gn_full_b1 -f python tools/profile_unet.py --batch 1 > /dev/null 2>&1
-for f in igemm_full_b8 igemm_full_b1 attn_gn_full_b8 attn_gn_full_b1; do python tools/ncu_summary.py $O/$f.ncu-rep > $O/$f.txt 2>&1; done
+for f in igemm_full_b8 igemm_full_b1 attn_gn_full_b8 attn_gn_full_b1; do
+  python tools/ncu_summary.py $O/$f.ncu-rep > $O/$f.txt 2>&1
+  rm -f $O/$f.ncu-rep      # ~1.7 MB per captured launch: only the summaries travel back (64 MiB limit)
+done
 du -sh $O; ls -la $O

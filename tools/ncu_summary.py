@@ -16,6 +16,10 @@ COLS = [
     ("sm__cycles_elapsed.max", "cycles"),
     ("launch__registers_per_thread", "regs"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_pct"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "mufu_pct"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
 ]
 
 
@@ -36,6 +40,22 @@ def main():
                 else:
                     vals.append("-")
             print(f"{name} | {r[col['Grid Size']]} | " + " | ".join(vals))
+        # top warp-stall reasons, first launch of every kernel name
+        seen = set()
+        stall_cols = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_warp_active.pct")]
+        for r in rows[2:]:
+            name = r[col["Kernel Name"]].split("(")[0]
+            if name in seen or not stall_cols:
+                continue
+            seen.add(name)
+            vals = []
+            for h in stall_cols:
+                try:
+                    vals.append((float(r[col[h]].replace(",", "")), h.split("issue_stalled_")[1].split("_per_warp")[0]))
+                except ValueError:
+                    pass
+            vals.sort(reverse=True)
+            print(f"  stalls {name}: " + ", ".join(f"{n} {v:.0f}%" for v, n in vals[:7]))
 
 
 if __name__ == "__main__":
