@@ -494,50 +494,29 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         // MMA-only rate, measured with the operand loads left out -- tools/bench_ingest.py: 57 % / 65 % / 77 % of
         // 2 * 4096 MAC/clk at BN 128 / 160 / 256, i.e. a fixed ~58 cycles per M=128, K=16 instruction on top of
         // 0.42 * BN, also with cta_group::2 -- so wide tiles are what keeps the tensor pipe busy, not the issue loop.)
-        int kb = kb_begin;
-        while (kb < kb_end) {
-          const bool two = kb + 1 < kb_end;
-          const int s0 = stage;
-          const uint32_t ph0 = phase;
-          int s1 = s0 + 1;
-          uint32_t ph1 = ph0;
-          if (s1 == kStages) {
-            s1 = 0;
-            ph1 ^= 1;
-          }
-          const uint64_t ad0 = desc_base + (a_lo + s0 * (kABytes >> 4));
-          const uint64_t bd0 = desc_base + (b_lo + s0 * (Cfg::kBBytes >> 4));
-          const uint64_t ad1 = desc_base + (a_lo + s1 * (kABytes >> 4));
-          const uint64_t bd1 = desc_base + (b_lo + s1 * (Cfg::kBBytes >> 4));
-          mbar_wait(&full_bar[s0], ph0);
-          if (two) mbar_wait(&full_bar[s1], ph1);
+        // One k-block (4 MMAs) per barrier wait.  Issuing two k-blocks per trip was measured and dropped: the
+        // MMA-only rate (operand loads left out, tools/bench_ingest.py) stays at 57 % / 65 % / 77 % of 4096 MAC/clk
+        // for BN 128 / 160 / 256 either way -- a fixed ~58 cycles per M=128, K=16 instruction on top of 0.42 * BN,
+        // also with cta_group::2 -- and the batch-1 forward got 1.4 % slower (the first MMA waits for two stages).
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          const uint64_t adesc = desc_base + (a_lo + stage * (kABytes >> 4));
+          const uint64_t bdesc = desc_base + (b_lo + stage * (Cfg::kBBytes >> 4));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 field
             if constexpr (PAIR)
-              umma_bf16_2sm(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             else
-              umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          if constexpr (PAIR) umma_commit_2sm(&empty_bar[s0]);   // frees the stage in both CTAs
-          else umma_commit(&empty_bar[s0]);
-          stage = s1;
-          phase = ph1;
-          if (two) {
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              if constexpr (PAIR) umma_bf16_2sm(d_tmem, ad1 + 2 * k, bd1 + 2 * k, idesc, 1u);
-              else umma_bf16(d_tmem, ad1 + 2 * k, bd1 + 2 * k, idesc, 1u);
-            }
-            if constexpr (PAIR) umma_commit_2sm(&empty_bar[s1]);
-            else umma_commit(&empty_bar[s1]);
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
+          if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage]);   // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
           }
-          kb += two ? 2 : 1;
         }
         if constexpr (PAIR) umma_commit_2sm(&tmem_full[acc]);
         else umma_commit(&tmem_full[acc]);

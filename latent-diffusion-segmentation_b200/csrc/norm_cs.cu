@@ -51,26 +51,47 @@ gn_apply_cs_kernel(const __nv_bfloat16* __restrict__ s0, int c0, const float* __
     ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
     be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
   }
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) gstat[i] = 0.f;
-  __syncthreads();
   pdl_sync();
-  // group moments from the producer's channel moments.  One channel per thread and shared-memory atomics: all
-  // loads of the block are in flight together (ONE L2 round trip; a warp-per-group loop paid three in a row,
-  // ~1.2 us of the ~5 us this kernel takes at batch 1).
+  // group moments from the producer's channel moments: one warp per group, several groups per warp.  All loads of
+  // a warp's groups are issued before the first reduction, so the phase costs ONE L2 round trip instead of one per
+  // group.  (Shared-memory float atomics -- one channel per thread -- were tried and cost 10 us per launch inside
+  // the forward graph: profiles/r01_ablate_unet_b1_v12_gn_atomics.log.)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float inv_cnt = 1.f / (static_cast<float>(cpg) * static_cast<float>(hw));
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float2 v = c < c0 ? __ldcg(reinterpret_cast<const float2*>(cs0 + (static_cast<size_t>(b) * c0 + c) * 2))
-                            : __ldcg(reinterpret_cast<const float2*>(cs1 + (static_cast<size_t>(b) * c1 + (c - c0)) * 2));
-    const int g = c / cpg;
-    atomicAdd(&gstat[2 * g], v.x);
-    atomicAdd(&gstat[2 * g + 1], v.y);
-  }
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    const float mean = gstat[2 * threadIdx.x] * inv_cnt;
-    const float var = fmaxf(gstat[2 * threadIdx.x + 1] * inv_cnt - mean * mean, 0.f);
-    gstat[2 * threadIdx.x] = mean;
-    gstat[2 * threadIdx.x + 1] = rsqrtf(var + eps);
+  constexpr int kGroupsPerTrip = 4, kChanPerLane = 4;   // covers 32 groups on >= 8 warps, <= 128 channels per group
+  for (int g0 = warp; g0 < groups; g0 += nw * kGroupsPerTrip) {
+    float su[kGroupsPerTrip], sq[kGroupsPerTrip];
+#pragma unroll
+    for (int i = 0; i < kGroupsPerTrip; ++i) {
+      const int g = g0 + i * nw;
+      su[i] = 0.f;
+      sq[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kChanPerLane; ++k) {
+        const int c = g * cpg + lane + 32 * k;
+        if (g < groups && lane + 32 * k < cpg) {
+          const float2 v = c < c0 ? __ldcg(reinterpret_cast<const float2*>(cs0 + (static_cast<size_t>(b) * c0 + c) * 2))
+                                  : __ldcg(reinterpret_cast<const float2*>(cs1 + (static_cast<size_t>(b) * c1 + (c - c0)) * 2));
+          su[i] += v.x;
+          sq[i] += v.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kGroupsPerTrip; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        su[i] += __shfl_xor_sync(0xffffffffu, su[i], o);
+        sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+      }
+      const int g = g0 + i * nw;
+      if (lane == 0 && g < groups) {
+        const float mean = su[i] * inv_cnt;
+        const float var = fmaxf(sq[i] * inv_cnt - mean * mean, 0.f);
+        gstat[2 * g] = mean;
+        gstat[2 * g + 1] = rsqrtf(var + eps);
+      }
+    }
   }
   __syncthreads();
   float sc[8], sh[8];
@@ -131,7 +152,7 @@ extern "C" int ldmseg_groupnorm_apply_cs(const void* src0, int c0, const float* 
   LDM_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm_apply_cs: channels must be multiples of 8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int C8 = C / 8;
-  LDM_REQUIRE(C8 <= 512, "groupnorm_apply_cs: at most 4096 channels");
+  LDM_REQUIRE(C8 <= 512 && C / groups <= 128, "groupnorm_apply_cs: at most 4096 channels, 128 per group");
   // block = C8 * lanes threads, about 384 wide
   int lanes = 384 / C8;
   if (lanes < 1) lanes = 1;

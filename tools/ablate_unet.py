@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--size", type=int, default=64)
     ap.add_argument("--per-op", action="store_true")
+    ap.add_argument("--full-only", action="store_true", help="time the whole graph only (A/B of two builds)")
     args = ap.parse_args()
     from bench import build_models
     from ldmseg import _native as nat
@@ -68,6 +69,10 @@ def main():
 
     full = time_graph(runner([True] * len(ops)))
     print(f"full graph: {full * 1e3:.1f} us, {len(ops)} ops")
+    if args.full_only:
+        more = [time_graph(runner([True] * len(ops)), reps=20) for _ in range(3)]
+        print("full graph again: " + " ".join(f"{t * 1e3:.1f}" for t in more) + " us")
+        return
     fam = lambda t: t.split(":")[0]
     rows = lambda t: int(t.split(":")[1])
     groups = collections.OrderedDict()
