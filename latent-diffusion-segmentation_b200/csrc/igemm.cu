@@ -490,10 +490,6 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        // Two k-blocks per trip: half the barrier polls and address arithmetic per MMA.  (It does not change the
-        // MMA-only rate, measured with the operand loads left out -- tools/bench_ingest.py: 57 % / 65 % / 77 % of
-        // 2 * 4096 MAC/clk at BN 128 / 160 / 256, i.e. a fixed ~58 cycles per M=128, K=16 instruction on top of
-        // 0.42 * BN, also with cta_group::2 -- so wide tiles are what keeps the tensor pipe busy, not the issue loop.)
         // One k-block (4 MMAs) per barrier wait.  Issuing two k-blocks per trip was measured and dropped: the
         // MMA-only rate (operand loads left out, tools/bench_ingest.py) stays at 57 % / 65 % / 77 % of 4096 MAC/clk
         // for BN 128 / 160 / 256 either way -- a fixed ~58 cycles per M=128, K=16 instruction on top of 0.42 * BN,
