@@ -259,7 +259,8 @@ def run_group(group):
     elif group in ("attn_simple", "attn"):
         simple = group == "attn_simple"
         cases = [(1, 256, 8, 40), (2, 64, 8, 160), (1, 256, 8, 160), (1, 1024, 8, 80),
-                 (1, 4096, 8, 40), (2, 1024, 4, 40)]
+                 (1, 4096, 8, 40), (2, 1024, 4, 40), (1, 200, 8, 40), (1, 1000, 2, 80), (3, 320, 8, 80),
+                 (1, 4096 + 96, 1, 40)]   # ragged token counts: masked key columns, partial query tiles
         for (nb, ntok, heads, d) in cases:
             C = heads * d
             qkv = rnd(nb * ntok, 3 * C, scale=1.5)
