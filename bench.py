@@ -292,15 +292,17 @@ def kernel_roofline(sampler, peaks):
     ig_ms = max(full_ms - rest_ms, 1e-6)
     n = sum(is_ig)
     achieved = flops / (ig_ms / 1e3) / 1e12
-    traffic = None
+    # dram bytes per launch of this kernel from the committed ncu --set full capture (tools/make_traffic_json.py)
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "igemm_dram_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f)
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("traffic"), f"{tj.get('source')}: {tj.get('unit')}, {tj.get('launches_captured')} launches"
     return {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv3x3/conv1x1/linear)",
             "achieved": round(achieved, 2), "peak": peaks["burst"], "unit": "TFLOP/s",
             "peak_kind": f"burst, {peaks['source']}", "frac": round(achieved / peaks["burst"], 4),
-            "traffic": traffic, "launches": n, "algorithmic_gflop_per_launch": round(flops / 1e9 / max(n, 1), 2),
+            "traffic": traffic, "traffic_source": traffic_src, "launches": n, "algorithmic_gflop_per_launch": round(flops / 1e9 / max(n, 1), 2),
             "algorithmic_gflop_per_forward": round(flops / 1e9, 1), "avg_launch_us": round(ig_ms * 1e3 / max(n, 1), 2),
             "share_of_unet_forward": round(ig_ms / full_ms, 3), "unet_forward_ms_graph": round(full_ms, 3),
             "method": "in-graph: CUDA-event time of the UNet-forward graph minus the same graph without its "
