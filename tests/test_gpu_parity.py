@@ -226,3 +226,36 @@ def test_end_to_end_generate(dev, unets):
     ids3, prob3 = vs.decode_ids(lat)
     assert (logits.argmax(1) == ids3.long()).float().mean().item() >= 0.995
     torch.testing.assert_close(prob3, logits.softmax(1).max(1)[0], rtol=0, atol=2e-2)
+
+
+def test_latent128_forward_and_ddpm_run(dev, unets):
+    """BASELINE config #5 geometry: 1024x1024 RGB -> 128x128 latent (16384 tokens at the first attention level).
+    One UNet forward against the fp32 oracle (rel-L2 <= 2e-2), then encode -> 3 DDPM steps -> decode through
+    the public sampler: shapes, finiteness and agreement of the fused ids with argmax of the full logits."""
+    from ldmseg.engine.sampler import B200Sampler
+    from ldmseg.models import GeneralVAEImage, GeneralVAESeg
+    from ldmseg.schedulers import DDIMNoiseScheduler
+    from oracle.make_golden import SCHED_KW, VAE_KW
+    oracle_unet, unet = unets
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 12, 128, 128, generator=g)
+    tt = torch.tensor(509)
+    y = unet(x.to(dev), tt.to(dev), encoder_hidden_states=None).sample
+    with torch.no_grad():
+        ref = oracle_unet(x, tt).sample
+    r = rel_l2(y, ref)
+    print(f"unet forward 128x128 latent: rel_l2={r:.3e}")
+    assert y.shape == ref.shape and r <= 2e-2
+    torch.manual_seed(1)
+    vi = GeneralVAEImage().to(dev)
+    vs = GeneralVAESeg(**dict(VAE_KW, scaling_factor=0.18215)).to(dev)
+    sampler = B200Sampler(unet, DDIMNoiseScheduler(**SCHED_KW), vi, vs)
+    rgb = torch.rand(1, 3, 1024, 1024, generator=torch.Generator().manual_seed(4)).to(dev)
+    rgb_lat = sampler.encode_rgb(rgb)
+    assert tuple(rgb_lat.shape) == (1, 4, 128, 128) and torch.isfinite(rgb_lat).all()
+    lat = sampler.sample(rgb_lat, 4, seed=42, ddpm=True)
+    assert tuple(lat.shape) == (1, 4, 128, 128) and torch.isfinite(lat).all()
+    ids, prob = vs.decode_ids(lat * (1.0 / vs.scaling_factor))
+    assert tuple(ids.shape) == (1, 1024, 1024) and ids.dtype == torch.uint8
+    logits = vs.decode(lat * (1.0 / vs.scaling_factor))
+    assert (logits.argmax(1) == ids.long()).float().mean().item() >= 0.995
