@@ -213,8 +213,9 @@ def run_ours(args):
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}, all-gather of ids per step",
                    "l2": "bf16 weights streamed per UNet forward (1.63 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": round(e2e_value, 4), "unit": "masks/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                "h2d_bytes_per_step": int(host_rgb.numel() * 4), "d2h_bytes_per_step": int(B * S * S * (1 + 4))},
-        "gpu_launches": int(launches_per_step * args.steps),
+                "h2d_bytes_per_step": int(world * host_rgb.numel() * 4),
+                "d2h_bytes_per_step": int(world * B * S * S * (1 + 4)), "bytes_are": "whole job (all ranks)"},
+        "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_are": "per rank, whole timed region",
         "clocks": clock_info,
         "roofline": roof,
         "roofline_step": {"bound": "tensor", "achieved": round(per_gpu_masks * FLOP_PER_MASK / 1e12, 2),
