@@ -177,7 +177,16 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    # LDMSEG_PROFILE=1: bracket the timed region with cudaProfilerStart/Stop so that
+    # `ncu --profile-from-start off --metrics gpu__time_duration.sum -c N python bench.py ...` lists exactly the
+    # launches of the timed region (numbers printed by such a run are not bench values)
+    prof = os.environ.get("LDMSEG_PROFILE") == "1"
+    if prof:
+        torch.cuda.profiler.start()
     ms = timed(step_device, args.steps)
+    if prof:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     clock_info = clocks.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()

@@ -15,6 +15,9 @@ for b in 1 8; do
   timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_unet_b$b.csv python tools/profile_unet.py --batch $b > /dev/null 2>&1
   python tools/summarize_launches.py $O/launches_unet_b$b.csv > $O/launches_unet_b$b.txt 2>&1
 done
+# launch list of the bench command itself: the first 1400 launches of its timed region (encode + ~5 DDIM steps)
+LDMSEG_PROFILE=1 timeout 400 $NCU --metrics gpu__time_duration.sum --csv -c 1400 --log-file $O/launches_bench_b1.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+python tools/summarize_launches.py $O/launches_bench_b1.csv > $O/launches_bench_b1.txt 2>&1
 for w in encode decode; do
   timeout 300 $NCU --metrics gpu__time_duration.sum --csv --log-file $O/launches_$w.csv python tools/profile_unet.py --what $w > /dev/null 2>&1
   python tools/summarize_launches.py $O/launches_$w.csv > $O/launches_$w.txt 2>&1
