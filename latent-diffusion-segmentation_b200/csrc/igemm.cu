@@ -27,7 +27,13 @@ namespace ldm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kIgemmThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps
+// TMA warp, MMA warp, 8 epilogue warps -- 16 for the GEGLU epilogue without split-K: with K of only 320-1280 the
+// epilogue of a 128 x 256 tile (two MUFU and ~9 packed-FMA instructions per output) took longer than the tile's MMAs
+// and two warps per scheduler left it latency-bound (ncu at batch 8: issue 52 %, tensor 29 %; 87 -> 64 us at
+// M = 32768, K = 320, N = 2560).  The plain epilogue gains nothing from 16 warps (measured: it is bound by the
+// rate of its 32-byte sector stores at wide N, not by latency) and the batch-1 forward loses 0.7 %.
+__host__ __device__ constexpr int igemm_epi_warps(bool geglu, bool split) { return (geglu && !split) ? 16 : 8; }
+__host__ __device__ constexpr int igemm_threads(bool geglu, bool split) { return 64 + 32 * igemm_epi_warps(geglu, split); }
 constexpr int kABytes = BM * BK * 2;  // 16 KB per stage
 
 struct alignas(64) IgemmKParams {
@@ -88,8 +94,6 @@ struct IgemmCfg {
 //     column sum per lane (31 shuffles per quantity), then one red.global per (lane, quantity).
 // Eight epilogue warps: two per TMEM lane quadrant, taking alternate 32-column chunks of the tile.
 enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2 };
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
 
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // GELU(x) = x/2 (1 + erf(x/sqrt2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
@@ -104,6 +108,25 @@ __device__ __forceinline__ float fast_gelu(float x) {
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = 1.f - poly * t * __expf(-z * z);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+// Two GELUs per call on the packed-fp32x2 pipe (same Abramowitz-Stegun formula): 18 instructions per PAIR instead of
+// ~17 per value.  gelu(x) = x/2 + |x|/2 * erf(|x|/sqrt2), |x|/2 = z/sqrt2 with z = |x|/sqrt2.
+__device__ __forceinline__ float2 fast_gelu2(float2 x) {
+  const float2 z = make_float2(fabsf(x.x) * 0.70710678118654752440f, fabsf(x.y) * 0.70710678118654752440f);
+  const float2 den = f2_fma(z, f2_splat(0.3275911f), f2_splat(1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 poly = f2_fma(f2_splat(-1.061405429f), t, f2_splat(1.453152027f));   // negated polynomial: -(a5 t + a4) ...
+  poly = f2_fma(poly, t, f2_splat(-1.421413741f));
+  poly = f2_fma(poly, t, f2_splat(0.284496736f));
+  poly = f2_fma(poly, t, f2_splat(-0.254829592f));
+  poly = f2_mul(poly, t);
+  const float2 arg = f2_mul(f2_mul(z, f2_splat(-1.4426950408889634f)), z);     // -z^2 * log2(e)
+  const float2 e = make_float2(ex2_approx_f(arg.x), ex2_approx_f(arg.y));
+  const float2 erf_abs = f2_fma(poly, e, f2_splat(1.f));                        // 1 - poly(t) * exp(-z^2)
+  const float2 hx = f2_mul(x, f2_splat(0.5f));
+  const float2 hax = f2_mul(z, f2_splat(0.70710678118654752440f));              // |x| / 2
+  return f2_fma(hax, erf_abs, hx);
 }
 
 // Epilogue arguments held in registers (reading them through the parameter block from inside the loops
@@ -158,8 +181,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
       // chunk columns are [16 x h | 16 x g] -> 16 outputs = one 32-byte sector
       uint32_t o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o[i] = pack_bf16x2(v[2 * i] * fast_gelu(v[16 + 2 * i]), v[2 * i + 1] * fast_gelu(v[17 + 2 * i]));
+      for (int i = 0; i < 8; ++i) {
+        const float2 r = f2_mul(make_float2(v[2 * i], v[2 * i + 1]),
+                                fast_gelu2(make_float2(v[16 + 2 * i], v[17 + 2 * i])));
+        o[i] = pack_bf16x2(r.x, r.y);
+      }
       if (row_ok)
         stg256(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + (col0 >> 1), o);
       return;
@@ -254,10 +280,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
   }
 }
 
-// One warp, one output tile: processes the 32-column chunks half, half+2, ...
+// One warp, one output tile: processes the 32-column chunks half, half + NH, ...  (NH = epilogue warps per TMEM
+// lane quadrant)
 //   DIRECT : TMEM -> epilogue -> global            PARTIAL: TMEM -> split-K workspace
 //   FINAL  : sum of the workspace partials -> epilogue -> global, for the chunks dealt to this split
-template <int BN, bool GEGLU, int MODE>
+template <int BN, bool GEGLU, int MODE, int NH>
 __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, float* ws_tile, int split_idx,
                                               int m_base, int n0, int q, int half, int lane) {
   constexpr int kChunks = BN / 32;
@@ -267,7 +294,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
   const int img = m / p.HW;                                       // image of this row (per-image bias)
   const int img_stats = MODE == EPI_PARTIAL ? 0 : m_base / p.stats_hw;  // image of the warp's rows (statistics)
 #pragma unroll 1
-  for (int ch = half; ch < kChunks; ch += 2) {
+  for (int ch = half; ch < kChunks; ch += NH) {
     const int col0 = n0 + ch * 32;
     if (col0 >= p.N) break;
     float v[32];
@@ -305,9 +332,12 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
 }
 
 template <int BN, bool GEGLU, bool SPLIT, bool PAIR>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(igemm_threads(GEGLU, SPLIT), 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
   using Cfg = IgemmCfg<BN, PAIR>;
+  constexpr int kEpiWarps = igemm_epi_warps(GEGLU, SPLIT);
+  constexpr int kEpiThreads = kEpiWarps * 32;
+  constexpr int NH = kEpiWarps / 4;
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -551,7 +581,12 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if constexpr (!SPLIT) {
-        epilogue_warp<BN, GEGLU, EPI_DIRECT>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane);
+        if (p.debug & 32) {   // development only: drop the tile (is the epilogue the bottleneck?)
+          tc_fence_before();
+          release_acc(acc);
+          continue;
+        }
+        epilogue_warp<BN, GEGLU, EPI_DIRECT, NH>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane);
         tc_fence_before();
         release_acc(acc);
       } else {
@@ -559,7 +594,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         // tile have arrived, each split CTA reduces and finishes its share of the tile's chunks.
         float* ws_tile = p.workspace + static_cast<size_t>(tile) * p.split_k * (BM * BN);
         if (!(p.debug & 4))
-          epilogue_warp<BN, GEGLU, EPI_PARTIAL>(ea, t_row, ws_tile, split, m_base, n0, q, half, lane);
+          epilogue_warp<BN, GEGLU, EPI_PARTIAL, NH>(ea, t_row, ws_tile, split, m_base, n0, q, half, lane);
         tc_fence_before();
         release_acc(acc);
         // publish + wait for the peers: the CTA barrier orders every thread's partial stores before
@@ -579,7 +614,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (!(p.debug & 1))
-          epilogue_warp<BN, GEGLU, EPI_FINAL>(ea, 0, ws_tile, split, m_base, n0, q, half, lane);
+          epilogue_warp<BN, GEGLU, EPI_FINAL, NH>(ea, 0, ws_tile, split, m_base, n0, q, half, lane);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
           // the last CTA to finish its share re-arms both counters for the next launch
@@ -742,7 +777,7 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kIgemmThreads);
+  cfg.blockDim = dim3(igemm_threads(GEGLU, SPLIT));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

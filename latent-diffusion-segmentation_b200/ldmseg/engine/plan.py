@@ -32,7 +32,9 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
     m_tiles = (m + 127) // 128
     best, best_cost = (128, 1, False), float("inf")
     cands = [(bn, False) for bn in (256, 160, 128, 64)]
-    if allow_pair and m_tiles >= 2 and m_tiles % 2 == 0:
+    # (not for short K: there the epilogue bounds the kernel and coupling two CTAs' accumulator hand-over costs
+    # 10-14 %, measured at K = 320)
+    if allow_pair and m_tiles >= 2 and m_tiles % 2 == 0 and num_kb >= 10:
         cands = [(bn, True) for bn in (256, 160, 128)] + cands
     for bn, pair in cands:
         tiles = m_tiles * ((n + bn - 1) // bn)

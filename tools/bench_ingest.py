@@ -11,16 +11,17 @@ from ldmseg import _native as nat  # noqa: E402
 from ldmseg import _pack as pk  # noqa: E402
 
 
-def run_case(nb, h, w, cin, n, taps, bn, pair, debug, iters=20):
+def run_case(nb, h, w, cin, n, taps, bn, pair, debug, iters=20, act=0):
     dev = "cuda"
     m = nb * h * w
     x = torch.randn(m, cin, device=dev).to(torch.bfloat16)
     kp = taps * ((cin + 63) // 64 * 64)
     wt = pk.to_bf16(pk.tile_pack(torch.randn(n, kp, device=dev) * 0.02))
-    out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    n_out = n // 2 if act == nat.ACT_GEGLU else n
+    out = torch.empty(m, n_out, device=dev, dtype=torch.bfloat16)
     bias = torch.randn(n, device=dev)
-    p = nat.make_igemm_params([x], [cin], nb, h, w, [(0, taps)], wt, n, out, n, bias=bias, block_n=bn,
-                              weight_tiled=True, pair=pair)
+    p = nat.make_igemm_params([x], [cin], nb, h, w, [(0, taps)], wt, n, out, n_out, bias=bias, block_n=bn,
+                              weight_tiled=True, pair=pair, act=act)
     lib = nat.load()
     old = lib.ldmseg_set_debug(debug)
     try:
@@ -61,6 +62,18 @@ def main():
     torch.cuda.set_device(0)
     if len(sys.argv) > 1 and sys.argv[1] == "bn":
         return sweep_bn()
+    if len(sys.argv) > 1 and sys.argv[1] == "ff":
+        # transformer feed-forward shapes: short K, wide N -- epilogue / store bound?
+        for nb, h, w, cin, n, taps, bn, act in ((8, 1, 4096, 320, 2560, 1, 256, 2), (8, 1, 4096, 320, 2560, 1, 256, 0),
+                                                (8, 1, 4096, 1280, 320, 1, 160, 0), (8, 1, 1024, 640, 5120, 1, 256, 2),
+                                                (8, 1, 1024, 2560, 640, 1, 160, 0), (8, 1, 4096, 320, 960, 1, 256, 0)):
+            for pair in (False, True):
+                line = f"nb={nb} {h}x{w} cin={cin} n={n} bn={bn} act={act} pair={int(pair)}:"
+                for dbg, nm in ((0, "full"), (24, "noAB"), (32, "noEpi"), (56, "mmaOnly")):
+                    us, tf = run_case(nb, h, w, cin, n, taps, bn, pair, dbg, act=act)
+                    line += f"  {nm} {us:7.1f}us {tf:5.0f}TF"
+                print(line, flush=True)
+        return
     cases = [(8, 64, 64, 320, 320, 9, 160), (8, 32, 32, 640, 640, 9, 256), (8, 16, 16, 1280, 1280, 9, 256),
              (8, 1, 4096, 320, 2560, 1, 256), (8, 1, 4096, 1280, 320, 1, 160), (1, 64, 64, 320, 320, 9, 160),
              (1, 1, 8192, 4096, 4096, 1, 256)]
