@@ -796,6 +796,20 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (PAIR) {
+    // The persistent pair grid must be co-resident (split-K CTAs wait for their peers): never launch more
+    // clusters than the device can hold at once (a part with a half-populated TPC holds fewer than #SMs / 2).
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel<BN, GEGLU, SPLIT, PAIR>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms() / 2;
+      }
+      max_clusters = n;
+    }
+    if (grid > 2 * max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT, PAIR>, kp);
   if (e != cudaSuccess) {
     set_error("igemm_kernel launch: %s", cudaGetErrorString(e));

@@ -124,6 +124,13 @@ def test_weight_packing_is_a_valid_gemm_layout():
     torch.testing.assert_close(r[:, :, 1].reshape(5, 32), full[:, 32:], rtol=1e-3, atol=1e-3)
     wt, bt = pk.pack_convT2x2(torch.randn(8, 6, 2, 2, generator=g), torch.randn(6, generator=g))
     assert wt.shape == (24, 64) and bt.shape == (24,)
+    # block-tiled layout consumed by the TMA weight map: [N/16][K/64][16][64], rows zero-padded to 16
+    w2 = torch.randn(40, 192, generator=g)
+    tp = pk.tile_pack(w2)
+    assert tp.shape == (3, 3, 16, 64) and pk.TILE_ROWS == 16
+    for n, k in ((0, 0), (17, 70), (39, 191), (25, 128)):
+        assert tp[n // 16, k // 64, n % 16, k % 64] == w2[n, k]
+    assert tp[2, :, 8:, :].abs().sum() == 0          # rows 40..47 are padding
 
 
 def test_tiling_heuristic():
