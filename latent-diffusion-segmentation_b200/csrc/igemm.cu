@@ -9,14 +9,15 @@
 // FeedForward / Downsample2D / Upsample2D as called from /root/reference/ldmseg/models/unet.py:357,
 // 361-373, 388-395, 401-425, 431, and the convs of GeneralVAESeg.decode (models/vae.py:133-172).
 //
-// CTA = 192 threads, persistent over (tile, k-split) work items:
-//   warp 0      TMA producer   (one elected lane)
-//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5  epilogue: tcgen05.ld -> bias / row-bias / residual / SiLU / GEGLU -> global
+// CTA = 320 threads (576 for the GEGLU epilogue), persistent over (tile, k-split) work items:
+//   warp 0       TMA producer   (one elected lane)
+//   warp 1       TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..9   epilogue: tcgen05.ld -> bias / row-bias / residual / SiLU / GEGLU / GroupNorm statistics -> global
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages
 // (tmem_full/tmem_empty) between MMA and epilogue so tile i's epilogue overlaps tile i+1's MMAs.
 //
 // Tile: BLOCK_M = 128 output pixels x BN output channels, BLOCK_K = 64 (one 128-byte swizzle row).
+// PAIR variant: two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2) -- see IgemmCfg.
 #include "common.h"
 #include <cstdlib>
 #include <cstring>
@@ -59,10 +60,11 @@ struct alignas(64) IgemmKParams {
   int* counters;
   float* stats;       // optional per-(image, channel) {sum, sum of squares} of the stored output
   int stats_hw;       // rows per image for the statistics (the producer may be a plain [M, K] GEMM)
-  int w_tiled;        // weights stored as [N/32][K/64][32][64] blocks (4 KB contiguous per block)
+  int w_tiled;        // weights stored as [N/16][K/64][16][64] blocks (2 KB contiguous per block)
   int prefetch_b;     // issue the first work item's weight loads before the grid-dependency wait
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
-  int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store
+  int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store,
+                      // bit3 / bit4 leave the A / B loads out after a work item's first k-block, bit5 drop the epilogue
 };
 
 // PAIR: two CTAs of a cluster work as one 256 x BN tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
