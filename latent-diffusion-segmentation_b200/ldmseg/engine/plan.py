@@ -3,6 +3,7 @@ helpers that append kernel launches (igemm / GroupNorm / LayerNorm / resnet bloc
 channel-last buffers."""
 from __future__ import annotations
 
+import json
 import os
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -20,8 +21,25 @@ FUSE_GN_STATS = os.environ.get("LDMSEG_FUSE_GN_STATS", "1") != "0"
 USE_PAIR = os.environ.get("LDMSEG_PAIR", "1") != "0"     # CTA pairs (tcgen05 cta_group::2) where the model prefers them
 
 
+USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
+_TUNED: Optional[Dict[str, list]] = None
+
+
+def _tuned_table() -> Dict[str, list]:
+    """Measured (block_n, split_k, pair) per (M, N, k-blocks) from tools/tune_tiling.py; empty if absent."""
+    global _TUNED
+    if _TUNED is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_b200.json")
+        try:
+            with open(path) as f:
+                _TUNED = json.load(f).get("entries", {})
+        except (OSError, ValueError):
+            _TUNED = {}
+    return _TUNED
+
+
 def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
-                  allow_pair: bool = False) -> Tuple[int, int, bool]:
+                  allow_pair: bool = False, use_tuned: bool = True) -> Tuple[int, int, bool]:
     """Pick (block_n, split_k, pair) for an igemm of M x N with num_kb 64-wide K blocks.
 
     Cycle model per work item (one CTA, one 128 x bn output tile, one K split):
@@ -29,6 +47,10 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
     items run in waves of `sms` CTAs.  A CTA pair (cta_group::2, 256 x bn tile) stages only bn/2 rows of B per CTA
     (a measured per-k-block saving, against a fixed cluster-launch cost); it needs an even number of 128-row tiles.  Split-K (partials to a workspace, cooperative reduce) is considered
     only when the tiles cannot fill the machine, and is charged for the partial store and the reduction."""
+    if use_tuned and USE_TUNED and allow_split and sms == SMS:
+        hit = _tuned_table().get(f"{m},{n},{num_kb}")
+        if hit is not None and (allow_pair or not hit[2]):
+            return int(hit[0]), int(hit[1]), bool(hit[2])
     m_tiles = (m + 127) // 128
     best, best_cost = (128, 1, False), float("inf")
     cands = [(bn, False) for bn in (256, 160, 128, 64)]

@@ -144,3 +144,25 @@ def test_tiling_heuristic():
     assert split == 1
     bn, split, pair = choose_tiling(8 * 4096, 320, 45, allow_pair=True)   # ingest-bound conv: pair halves the B staging
     assert pair and bn in (128, 160, 256) and split == 1
+
+
+def test_tuned_tiling_table_is_legal():
+    """ldmseg/engine/tuned_b200.json (tools/tune_tiling.py): every measured override is a launch the kernel accepts
+    and the planner returns it; LDMSEG_TUNED=0 / use_tuned=False falls back to the cycle model."""
+    import json
+    from ldmseg.engine import plan
+    path = os.path.join(ROOT, "latent-diffusion-segmentation_b200", "ldmseg", "engine", "tuned_b200.json")
+    entries = json.load(open(path))["entries"]
+    assert entries
+    for key, (bn, split, pair, us_tuned, us_model) in entries.items():
+        m, n, kb = (int(v) for v in key.split(","))
+        m_tiles = (m + 127) // 128
+        tiles = m_tiles * ((n + bn - 1) // bn)
+        assert bn in (64, 128, 160, 256) and 1 <= split <= 16 and split <= kb
+        assert split == 1 or tiles * split <= 148                 # split-K CTAs must be co-resident
+        assert tiles * split * 128 * bn <= 16 * 1024 * 1024       # fits the plan's split-K workspace
+        if pair:
+            assert bn != 64 and m_tiles >= 2
+        assert us_tuned < us_model
+        assert plan.choose_tiling(m, n, kb, allow_pair=True) == (bn, split, bool(pair))
+        assert plan.choose_tiling(m, n, kb, allow_pair=True, use_tuned=False) != (bn, split, bool(pair))
