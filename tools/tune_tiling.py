@@ -78,13 +78,18 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "latent-diffusion-segmentation_b200", "ldmseg", "engine",
                                                   "tuned_b200.json"))
     ap.add_argument("--min-gain", type=float, default=0.04, help="keep an entry only if it beats the model's pick by this")
+    ap.add_argument("--merge", default=None, help="existing table whose entries are kept (other plans' shapes)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ws = torch.zeros(16 * 1024 * 1024, device="cuda")
     cnt = torch.zeros(8192, device="cuda", dtype=torch.int32)
     table = {}
+    if args.merge and os.path.exists(args.merge):
+        table = json.load(open(args.merge)).get("entries", {})
     total_model = total_best = 0.0
     for (m, n, kb), name in sorted(shapes_from_log(args.log).items()):
+        if f"{m},{n},{kb}" in table:
+            continue
         geglu = name.endswith("ff1")
         m_tiles = (m + 127) // 128
         cands = []
@@ -118,7 +123,7 @@ def main():
             table[f"{m},{n},{kb}"] = [best[0], best[1], int(best[2]), round(t_best, 2), round(t_model, 2)]
     print(f"sum over distinct shapes: model {total_model:.1f} us, best {total_best:.1f} us")
     with open(args.out, "w") as f:
-        json.dump({"device": torch.cuda.get_device_name(0), "source": os.path.relpath(args.log, ROOT),
+        json.dump({"device": torch.cuda.get_device_name(0), "source": "op tags of profiles/r01_ablate_unet_b{1,8}_v15.log",
                    "columns": ["block_n", "split_k", "pair", "us_tuned", "us_model"], "entries": table}, f, indent=1)
     print(f"wrote {len(table)} entries to {args.out}")
 
