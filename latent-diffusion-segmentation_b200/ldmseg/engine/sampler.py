@@ -14,7 +14,7 @@ What is different from driving `unet(...)` + `scheduler.step(...)` from Python:
     batch-uniform and known in advance) -> a [steps, 20160] table; each step selects its row;
   * one fused kernel does the scheduler update, writes the fp32 latent state, x0 and the next
     step's 16-channel bf16 UNet input (no torch.cat, no dtype cast, no .item());
-  * the step index lives in device memory, so ONE captured graph (≈ 400 kernel nodes) is replayed
+  * the step index lives in device memory, so ONE captured graph (267 kernel nodes) is replayed
     N times.
 Extensions that the reference lacks, both exact restatements of the oracle
 in oracle/ldmseg_restated.py: sampling-time inpainting (`mask`, `known_latents`) and ancestral
