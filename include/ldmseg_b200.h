@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LDMSEG_ABI_VERSION 1
+#define LDMSEG_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ldmseg_version(void);
@@ -96,6 +96,22 @@ typedef struct ldmseg_igemm_params {
   int pair;                          /* 1: CTA pairs (clusters of 2, tcgen05 cta_group::2): 256 x block_n tiles, each
                                         CTA stages its 128 rows of A and half of the B tile.  Needs weight_tiled,
                                         block_n in {128, 160, 256} and M > 128 */
+  /* ---- ABI version 2 ---- */
+  int weight_static;                 /* 1: nothing on the stream writes `weight` (real parameters), so its first
+                                        tiles may be fetched BEFORE the grid-dependency wait under `pdl`.  Must be 0
+                                        when the B operand was produced by an earlier launch (VAE attention K / V^T) */
+  const void* next_weight;           /* optional: weights of the NEXT igemm launch on the stream; each CTA pulls a
+                                        slice of it into L2 once its own operand loads are in flight (hint only) */
+  long long next_weight_bytes;
+  int residual_f32;                  /* 1: `residual` is f32 [M, res_ld] (fp32 residual stream) */
+  void* out2;                        /* optional bf16 [M, out2_ld] shadow of an f32 `out`: the copy that later launches
+                                        read through TMA (shortcut / down-sampling operands) */
+  int out2_ld;
+  int conv_stride;                   /* 0/1: stride 1 with zero padding 1.  2: 3x3 stride-2 convolution; (nb, h, w) is
+                                        the OUTPUT geometry, every source is [nb, 2h, 2w, c] and is read through the
+                                        TMA traversal stride (diffusers Downsample2D, unet.py:361-373; the
+                                        AutoencoderKL encoder's F.pad(0,1,0,1) + stride-2 conv) */
+  int conv_pad;                      /* stride 2 only: zero padding before (top / left): 1 (UNet) or 0 (VAE) */
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);
@@ -118,6 +134,11 @@ int ldmseg_groupnorm_apply_cs(const void* src0, int c0, const float* chan_stats0
                               int c1, const float* chan_stats1, int nb, int hw, int groups,
                               const float* gamma, const float* beta, float eps, int silu, void* out,
                               void* stream);
+/* Same, both sources f32 (the fp32 residual stream written by ldmseg_igemm with out_dtype F32). */
+int ldmseg_groupnorm_apply_cs_f32(const void* src0, int c0, const float* chan_stats0, const void* src1,
+                                  int c1, const float* chan_stats1, int nb, int hw, int groups,
+                                  const float* gamma, const float* beta, float eps, int silu, void* out,
+                                  void* stream);
 /* Launch every kernel of the library with programmatic dependent launch (prologue of kernel i+1
  * overlaps the tail of kernel i); returns the previous setting. */
 int ldmseg_set_pdl(int enable);
@@ -127,6 +148,9 @@ int ldmseg_set_debug(int flags);
  * BasicTransformerBlock.norm1/norm3 and LayerNorm2d (ldmseg/models/vae.py:309-322). */
 int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma, const float* beta,
                      float eps, int silu, void* out, void* stream);
+/* Same with an f32 source row (fp32 residual stream); output stays bf16 (a GEMM operand). */
+int ldmseg_layernorm_f32(const void* src, int rows, int c, const float* gamma, const float* beta,
+                         float eps, int silu, void* out, void* stream);
 
 /* Row softmax with scale (f32 scores -> bf16 probabilities): the fp32 softmax of diffusers 0.16.1
  * AttentionBlock (single head, d = 512) in the AutoencoderKL mid block. */
@@ -140,6 +164,13 @@ int ldmseg_softmax_rows(const float* s, int rows, int cols, float scale, void* o
 int ldmseg_attention(const void* qkv, int nb, int ntok, int heads, int d, void* out, void* stream);
 int ldmseg_attention_simple(const void* qkv, int nb, int ntok, int heads, int d, void* out,
                             void* stream);
+/* Cross-attention (diffusers BasicTransformerBlock.attn2; kept by the conditioned variants of
+ * ldmseg/models/descriptors.py:67-105 and driven with a doubled batch by the guidance path of
+ * ldmseg/trainers/trainers_ldm_cond.py:1098-1123,1143-1146): q is bf16 [nb*ntok_q, heads*d] (to_q of the
+ * image tokens), kv is bf16 [nb*ntok_kv, 2*heads*d] (to_k | to_v of encoder_hidden_states; 77 text or 257 image
+ * tokens: key columns beyond ntok_kv are masked), out is bf16 [nb*ntok_q, heads*d].  Same kernel as above. */
+int ldmseg_cross_attention(const void* q, const void* kv, int nb, int ntok_q, int ntok_kv, int heads,
+                           int d, void* out, void* stream);
 
 /* ---- element-wise / layout -------------------------------------------------------------- */
 /* h * gelu_erf(g) for x = [rows, 2*c] = (h | g): diffusers GEGLU. */
@@ -181,11 +212,16 @@ int ldmseg_ddim_step(const float* model_out, const float* sample, int64_t n, flo
  * The step index is read from device memory (*step_ptr) so one captured graph serves all steps;
  * coef is f32 [nsteps, 4] = (sqrt_a_t, sqrt_1ma_t, sqrt_a_prev, sqrt_1ma_prev); on the last step
  * the state becomes x0 (Q1 in SURVEY.md).  Optional inpainting blend (extension): mask f32 [M],
- * known f32 [M,4] (already noised to t_prev by the caller per step: known[step]). */
+ * known f32 [nsteps, M, 4] (already noised to t_prev by the caller per step: known[step]); optional ancestral
+ * noise f32 [nsteps, M, 4] with sigma f32 [nsteps] (DDPM extension).  prediction_type / clip / clip_range are the
+ * scheduler's (ddim_scheduler.py:238-257).  cfg = 1: classifier-free guidance (trainers_ldm_cond.py:1143-1146):
+ * eps is [2M,4] (uncond | cond rows), eps = e_u + guidance * (e_c - e_u), and the next UNet input is written for
+ * both halves (rows i and M + i); not defined together with self_cond (the reference's shapes do not allow it). */
 int ldmseg_sampler_step(const float* eps, float* latents, float* x0, const float* rgb_latents,
                         void* unet_in, int64_t m, const float* coef, const int* step_ptr,
                         int nsteps, int self_cond, const float* mask, const float* known,
-                        const float* noise, const float* sigma, void* stream);
+                        const float* noise, const float* sigma, int prediction_type, int clip,
+                        float clip_range, int cfg, float guidance, void* stream);
 int ldmseg_advance_step(int* step_ptr, void* stream);
 /* Same update as ldmseg_ddim_step, but the timestep is a 0-dim int64 tensor ON THE DEVICE and the
  * alphas_cumprod table (f32 [num_train_timesteps]) lives on the device too, so `step` needs no
@@ -195,6 +231,15 @@ int ldmseg_ddim_step_indexed(const float* model_out, const float* sample, int64_
                              int step_ratio, float final_alpha, int prediction_type, int clip,
                              float clip_range, int use_clipped, float* prev_sample, float* pred_x0,
                              void* stream);
+
+/* add_noise (mode 0) / remove_noise (mode 1) with PER-SAMPLE timesteps read on the device
+ * (ddim_scheduler.py:155-216; the training-step no-grad forward, trainers_ldm_cond.py:813-831):
+ *   mode 0: out = sqrt(a_t) * scale * x + sqrt(1 - a_t) * noise      mode 1: out = (x - sqrt(1 - a_t) * noise) / (sqrt(a_t) * scale)
+ * x / noise / out f32 [nb, per_sample]; timesteps int64 [nb] and alphas_cumprod f32 on the device.  Optional
+ * unet_in (mode 0, x = NCHW [nb, c, hw]): also writes channels [0, c) of the channel-last bf16 [nb*hw, cpad] UNet input. */
+int ldmseg_noise_mix(const float* x, const float* noise, const int64_t* timesteps_dev,
+                     const float* alphas_cumprod_dev, int nb, int64_t per_sample, float scale, int mode,
+                     float* out, void* unet_in, int hw, int cpad, void* stream);
 
 /* ---- time embedding --------------------------------------------------------------------- *
  * y[r, :] = act_out( W x_act(r) + b ), f32, small-batch (r = timesteps): Timesteps sinusoid,
@@ -220,6 +265,25 @@ int ldmseg_bilinear2x_to_nchw(const void* src, int src_is_f32, int nb, int h, in
  * (ldmseg/trainers/trainers_ldm_cond.py:428-433). */
 int ldmseg_bilinear2x_argmax(const void* src, int src_is_f32, int nb, int h, int w, int c, int ld,
                              uint8_t* ids, float* maxprob, void* stream);
+
+/* ---- panoptic post-processing (the per-image tail of compute_pq) --------------------------------- *
+ * Replaces ldmseg/trainers/trainers_ldm_cond.py:1261-1313, which resizes the 134 MB/image logits per image,
+ * copies the full [128, h, w] sigmoid map to the host and filters segments in numpy.
+ *   logits  f32 channel-last [nb, s, s, ld] (first c = 128 columns): the seg decoder's output BEFORE its bilinear
+ *           x2 (vae.py:270); the x2 and the per-image resize (:1267-1272) are composed inside the kernel.
+ *   geom    int32 [nb, 6] ON THE DEVICE = {h, w, crop_y0, crop_x0, crop_h, crop_w}: target size and the padding
+ *           crop (crop_padding, :1172-1178) on the 2s x 2s grid.  max_hw >= max h*w; out_stride = pixels per image
+ *           in pred / ids.
+ *   pred    int16 [nb, out_stride]: argmax class, -1 where the max softmax probability < mask_th (:1275-1284)
+ *   area / orig_area  int32 [nb, 128]: #pixels with pred == c / #pixels with sigmoid(logit_c) >= mask_th (:1301) */
+int ldmseg_panoptic_resample(const float* logits, int nb, int s, int c, int ld, const int* geom_dev,
+                             int max_hw, int out_stride, float mask_th, int threshold_output,
+                             int16_t* pred, int* area, int* orig_area, void* stream);
+/* keep[c] = area[c] >= count_th && c != ignore_label && area[c] / orig_area[c] >= overlap_th (:1293-1304);
+ * ids (u8 [nb, out_stride]) = keep[pred] ? pred + 1 : 0 (:1296-1313); keep int32 [nb, 128] = segments_info. */
+int ldmseg_panoptic_filter(const int16_t* pred, int nb, const int* geom_dev, int max_hw, int out_stride,
+                           const int* area, const int* orig_area, int count_th, double overlap_th,
+                           int ignore_label, uint8_t* ids, int* keep, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libldmseg_b200.so")
-SOURCES = ["common.cu", "igemm.cu", "attn.cu", "norm.cu", "norm_cs.cu", "elementwise.cu"]
+SOURCES = ["common.cu", "igemm.cu", "attn.cu", "norm.cu", "norm_cs.cu", "elementwise.cu", "panoptic.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

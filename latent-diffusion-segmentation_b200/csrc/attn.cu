@@ -49,6 +49,8 @@ struct alignas(64) AttnKParams {
   CUtensorMap map_kv;
   __nv_bfloat16* out;
   int nb, ntok, heads;
+  int ntok_kv;       // number of key / value tokens (= ntok for self-attention)
+  int k_which, v_which;  // index of K / V along the "which" dimension of map_kv (1, 2 in a fused QKV; 0, 1 in a KV tensor)
   float scale_log2;  // (1/sqrt(d)) * log2(e)
 };
 
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   const int head = (blockIdx.x / q_blocks) % p.heads;
   const int b = blockIdx.x / (q_blocks * p.heads);
   const int q0 = qb * 256;
-  const int T = (p.ntok + BKV - 1) / BKV;
+  const int T = (p.ntok_kv + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_q);
@@ -190,9 +192,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         mbar_expect_tx(&kv_full[st], 2 * Cfg::kKBytes);
         for (int pn = 0; pn < kPanels; ++pn) {
           tma_load_5d(sm_k + st * Cfg::kKBytes + pn * BKV * 128, &p.map_kv, &kv_full[st], pn * 64,
-                      head, 1, j * BKV, b);
+                      head, p.k_which, j * BKV, b);
           tma_load_5d(sm_v + st * Cfg::kKBytes + pn * BKV * 128, &p.map_kv, &kv_full[st], pn * 64,
-                      head, 2, j * BKV, b);
+                      head, p.v_which, j * BKV, b);
         }
       }
     }
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&s_free[t]);
-      const int kv_valid = p.ntok - j * BKV;  // columns < kv_valid are real tokens
+      const int kv_valid = p.ntok_kv - j * BKV;  // columns < kv_valid are real tokens
       if (kv_valid < BKV) {
 #pragma unroll
         for (int i = 0; i < BKV; ++i)
@@ -450,22 +452,31 @@ __global__ void attn_simple_kernel(const __nv_bfloat16* __restrict__ qkv, int nb
   }
 }
 
+// q_src: bf16 [nb*ntok, q_which_n * heads * D] (column block 0 = Q); kv_src: bf16 [nb*ntok_kv, kv_which_n * heads * D]
+// with K / V in column blocks k_which / v_which.  Self-attention: q_src = kv_src = the fused QKV, (3, 1, 2).
 template <int D, int PM>
-static int launch_attn_pm(const void* qkv, int nb, int ntok, int heads, void* out, cudaStream_t st) {
+static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which,
+                          int v_which, int nb, int ntok, int ntok_kv, int heads, void* out, cudaStream_t st) {
   using Cfg = AttnCfg<D>;
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));
   const uint64_t C = static_cast<uint64_t>(heads) * D;
-  uint64_t dims[5] = {static_cast<uint64_t>(D), static_cast<uint64_t>(heads), 3,
-                      static_cast<uint64_t>(ntok), static_cast<uint64_t>(nb)};
-  uint64_t strides[4] = {static_cast<uint64_t>(D) * 2, C * 2, 3 * C * 2, 3 * C * 2 * ntok};
+  uint64_t dims_q[5] = {static_cast<uint64_t>(D), static_cast<uint64_t>(heads), static_cast<uint64_t>(q_which_n),
+                        static_cast<uint64_t>(ntok), static_cast<uint64_t>(nb)};
+  uint64_t str_q[4] = {static_cast<uint64_t>(D) * 2, C * 2, q_which_n * C * 2, q_which_n * C * 2 * ntok};
+  uint64_t dims_kv[5] = {static_cast<uint64_t>(D), static_cast<uint64_t>(heads), static_cast<uint64_t>(kv_which_n),
+                         static_cast<uint64_t>(ntok_kv), static_cast<uint64_t>(nb)};
+  uint64_t str_kv[4] = {static_cast<uint64_t>(D) * 2, C * 2, kv_which_n * C * 2, kv_which_n * C * 2 * ntok_kv};
   uint32_t box_q[5] = {64, 1, 1, 128, 1};
   uint32_t box_kv[5] = {64, 1, 1, static_cast<uint32_t>(Cfg::BKV), 1};
-  if (int rc = encode_tmap_bf16(&kp.map_q, qkv, 5, dims, strides, box_q)) return rc;
-  if (int rc = encode_tmap_bf16(&kp.map_kv, qkv, 5, dims, strides, box_kv)) return rc;
+  if (int rc = encode_tmap_bf16(&kp.map_q, q_src, 5, dims_q, str_q, box_q)) return rc;
+  if (int rc = encode_tmap_bf16(&kp.map_kv, kv_src, 5, dims_kv, str_kv, box_kv)) return rc;
   kp.out = reinterpret_cast<__nv_bfloat16*>(out);
   kp.nb = nb;
   kp.ntok = ntok;
+  kp.ntok_kv = ntok_kv;
+  kp.k_which = k_which;
+  kp.v_which = v_which;
   kp.heads = heads;
   kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   static bool configured = false;
@@ -480,16 +491,27 @@ static int launch_attn_pm(const void* qkv, int nb, int ntok, int heads, void* ou
 }
 
 template <int D>
-static int launch_attn(const void* qkv, int nb, int ntok, int heads, void* out, cudaStream_t st) {
+static int launch_attn(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which, int v_which,
+                       int nb, int ntok, int ntok_kv, int heads, void* out, cudaStream_t st) {
   static int pm = -1;
   if (pm < 0) {
     const char* e = getenv("LDMSEG_ATTN_POLY");
     pm = e ? atoi(e) : 2;
   }
   switch (pm) {
-    case 0: return launch_attn_pm<D, 0>(qkv, nb, ntok, heads, out, st);
-    case 1: return launch_attn_pm<D, 1>(qkv, nb, ntok, heads, out, st);
-    default: return launch_attn_pm<D, 2>(qkv, nb, ntok, heads, out, st);
+    case 0: return launch_attn_pm<D, 0>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+    case 1: return launch_attn_pm<D, 1>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+    default: return launch_attn_pm<D, 2>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+  }
+}
+
+static int attn_dispatch(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which,
+                         int v_which, int nb, int ntok, int ntok_kv, int heads, int d, void* out, cudaStream_t st) {
+  switch (d) {
+    case 40: return launch_attn<40>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+    case 80: return launch_attn<80>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+    case 160: return launch_attn<160>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+    default: set_error("attention: unsupported head dim %d (40, 80, 160)", d); return -2;
   }
 }
 
@@ -501,13 +523,15 @@ extern "C" int ldmseg_attention(const void* qkv, int nb, int ntok, int heads, in
                                 void* stream) {
   LDM_REQUIRE(qkv && out && nb > 0 && ntok > 0 && heads > 0, "attention: bad arguments");
   LDM_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "attention: qkv not 16-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (d) {
-    case 40: return launch_attn<40>(qkv, nb, ntok, heads, out, st);
-    case 80: return launch_attn<80>(qkv, nb, ntok, heads, out, st);
-    case 160: return launch_attn<160>(qkv, nb, ntok, heads, out, st);
-    default: set_error("attention: unsupported head dim %d (40, 80, 160)", d); return -2;
-  }
+  return attn_dispatch(qkv, 3, qkv, 3, 1, 2, nb, ntok, ntok, heads, d, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ldmseg_cross_attention(const void* q, const void* kv, int nb, int ntok_q, int ntok_kv, int heads,
+                                      int d, void* out, void* stream) {
+  LDM_REQUIRE(q && kv && out && nb > 0 && ntok_q > 0 && ntok_kv > 0 && heads > 0, "cross_attention: bad arguments");
+  LDM_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0,
+              "cross_attention: q / kv not 16-byte aligned");
+  return attn_dispatch(q, 1, kv, 2, 0, 1, nb, ntok_q, ntok_kv, heads, d, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ldmseg_attention_simple(const void* qkv, int nb, int ntok, int heads, int d, void* out,

@@ -3,6 +3,8 @@
 
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "../../include/ldmseg_b200.h"
 
@@ -39,7 +41,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box) {
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver / no GPU?)");
@@ -52,8 +54,34 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  // Descriptor cache: a launch list is issued again and again over the same buffers (the un-captured drop-in path
+  // re-encoded up to four maps per igemm launch); the encoded map depends only on the arguments below.
+  struct Key {
+    uint64_t base, dims[5], strides[4];
+    uint32_t rank, box[5], estr[5];
+  } key;
+  memset(&key, 0, sizeof(key));
+  key.base = reinterpret_cast<uint64_t>(base);
+  key.rank = static_cast<uint32_t>(rank);
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = gdim[i];
+    key.box[i] = bdim[i];
+    key.estr[i] = estr[i];
+    if (i > 0) key.strides[i - 1] = gstr[i - 1];
+  }
+  static std::mutex mu;
+  static std::unordered_map<std::string, CUtensorMap> cache;
+  const std::string ks(reinterpret_cast<const char*>(&key), sizeof(key));
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(ks);
+    if (it != cache.end()) {
+      *map = it->second;
+      return 0;
+    }
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                   const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -66,6 +94,11 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
               (unsigned long long)(rank > 3 ? gdim[3] : 0), bdim[0], rank > 1 ? bdim[1] : 0,
               rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0);
     return -4;
+  }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > (1u << 16)) cache.clear();
+    cache.emplace(ks, *map);
   }
   return 0;
 }

@@ -67,8 +67,10 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 
 // Encode a tiled, 128B-swizzled bf16 tensor map of the given rank (dims innermost first).
 // strides_bytes has rank-1 entries (stride of dims 1..rank-1).  Returns 0 on success.
+// elem_strides (optional, rank entries): traversal stride per dimension -- with stride s a box of s * n
+// traversed elements lands as n elements in shared memory (strided convolutions without im2col).
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box);
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 inline int num_sms() {
   static int n = 0;

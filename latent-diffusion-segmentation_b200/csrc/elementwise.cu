@@ -186,13 +186,16 @@ __global__ void ddim_step_kernel(const float* __restrict__ mo, const float* __re
 }
 
 // Fused sampler step over pixels (one thread per pixel, 4 latent channels as float4).
+// cfg: classifier-free guidance (trainers_ldm_cond.py:1143-1146): eps holds 2m rows (uncond | cond) and the next
+// UNet input is written twice (rows i and m + i), as `torch.cat([latents] * 2)` does.
 __global__ void sampler_step_kernel(const float4* __restrict__ eps, float4* __restrict__ lat,
                                     float4* __restrict__ x0o, const float4* __restrict__ rgb,
                                     uint4* __restrict__ unet_in, long long m,
                                     const float* __restrict__ coef, const int* __restrict__ step_ptr,
                                     int nsteps, int self_cond, const float* __restrict__ mask,
                                     const float4* __restrict__ known, const float4* __restrict__ noise,
-                                    const float* __restrict__ sigma) {
+                                    const float* __restrict__ sigma, int ptype, int clip, float clip_range,
+                                    int cfg, float guidance) {
   pdl_sync();
   const int step = *step_ptr;
   const float sa_t = coef[step * 4 + 0], sb_t = coef[step * 4 + 1];
@@ -201,13 +204,18 @@ __global__ void sampler_step_kernel(const float4* __restrict__ eps, float4* __re
   const float sg = (sigma != nullptr) ? sigma[step] : 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < m;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 e = eps[i];
+    float4 e = eps[i];
+    if (cfg) {
+      const float4 et = eps[m + i];
+      e.x += guidance * (et.x - e.x); e.y += guidance * (et.y - e.y);
+      e.z += guidance * (et.z - e.z); e.w += guidance * (et.w - e.w);
+    }
     const float4 x = lat[i];
     float4 pv, x0;
-    ddim_update(e.x, x.x, sa_t, sb_t, sa_p, sb_p, 0, 0, 1.f, 0, pv.x, x0.x);
-    ddim_update(e.y, x.y, sa_t, sb_t, sa_p, sb_p, 0, 0, 1.f, 0, pv.y, x0.y);
-    ddim_update(e.z, x.z, sa_t, sb_t, sa_p, sb_p, 0, 0, 1.f, 0, pv.z, x0.z);
-    ddim_update(e.w, x.w, sa_t, sb_t, sa_p, sb_p, 0, 0, 1.f, 0, pv.w, x0.w);
+    ddim_update(e.x, x.x, sa_t, sb_t, sa_p, sb_p, ptype, clip, clip_range, 0, pv.x, x0.x);
+    ddim_update(e.y, x.y, sa_t, sb_t, sa_p, sb_p, ptype, clip, clip_range, 0, pv.y, x0.y);
+    ddim_update(e.z, x.z, sa_t, sb_t, sa_p, sb_p, ptype, clip, clip_range, 0, pv.z, x0.z);
+    ddim_update(e.w, x.w, sa_t, sb_t, sa_p, sb_p, ptype, clip, clip_range, 0, pv.w, x0.w);
     if (noise != nullptr && !last) {
       const float4 z = noise[static_cast<long long>(step) * m + i];
       pv.x += sg * z.x; pv.y += sg * z.y; pv.z += sg * z.z; pv.w += sg * z.w;
@@ -239,6 +247,41 @@ __global__ void sampler_step_kernel(const float4* __restrict__ eps, float4* __re
       b.z = b.w = 0;
       unet_in[2 * i] = a;
       unet_in[2 * i + 1] = b;
+      if (cfg) {
+        unet_in[2 * (m + i)] = a;
+        unet_in[2 * (m + i) + 1] = b;
+      }
+    }
+  }
+}
+
+// ---- add_noise / remove_noise with per-sample timesteps (ddim_scheduler.py:155-216) ----------------------------
+// x [nb, per] f32 (any layout with the sample index outermost), t int64 [nb] on the device, acp f32 table.
+// mode 0: out = sqrt(a) * scale * x + sqrt(1 - a) * noise          (add_noise)
+// mode 1: out = (x - sqrt(1 - a) * noise) / (sqrt(a) * scale)      (remove_noise)
+// unet_in (optional, mode 0, NCHW input with 4 channels): also writes channels [0,4) of the channel-last bf16
+// UNet input rows (the training-step no-grad forward, trainers_ldm_cond.py:824-831).
+__global__ void noise_mix_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                 const long long* __restrict__ t, const float* __restrict__ acp, int nb,
+                                 long long per, float scale, int mode, float* __restrict__ out,
+                                 __nv_bfloat16* __restrict__ unet_in, int hw, int cpad) {
+  pdl_sync();
+  const long long total = static_cast<long long>(nb) * per;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per);
+    const float a = acp[t[b]];
+    // the reference raises the gathered fp32 alphas to the power 0.5 (ddim_scheduler.py:171-176)
+    const float sa = sqrtf(a), sb = sqrtf(1.f - a);
+    float o;
+    if (mode == 0) o = sa * scale * x[i] + sb * noise[i];
+    else o = (x[i] - sb * noise[i]) / (sa * scale);
+    out[i] = o;
+    if (unet_in != nullptr) {
+      const long long r = i - static_cast<long long>(b) * per;   // c * hw + p
+      const int c = static_cast<int>(r / hw);
+      const long long pix = static_cast<long long>(b) * hw + (r - static_cast<long long>(c) * hw);
+      unet_in[pix * cpad + c] = __float2bfloat16(o);
     }
   }
 }
@@ -509,16 +552,36 @@ extern "C" int ldmseg_sampler_step(const float* eps, float* latents, float* x0,
                                    const float* rgb_latents, void* unet_in, int64_t m,
                                    const float* coef, const int* step_ptr, int nsteps, int self_cond,
                                    const float* mask, const float* known, const float* noise,
-                                   const float* sigma, void* stream) {
+                                   const float* sigma, int prediction_type, int clip, float clip_range,
+                                   int cfg, float guidance, void* stream) {
   LDM_REQUIRE(eps && latents && coef && step_ptr, "sampler_step: null pointer");
   LDM_REQUIRE(!unet_in || rgb_latents, "sampler_step: unet_in needs rgb_latents");
   LDM_REQUIRE(!mask || known, "sampler_step: mask needs known latents");
+  LDM_REQUIRE(prediction_type >= 0 && prediction_type <= 2, "sampler_step: bad prediction_type");
+  LDM_REQUIRE(!(cfg && self_cond), "sampler_step: guidance with self-conditioning is undefined in the reference "
+                                   "(trainers_ldm_cond.py:1126-1150 concatenates a 2B batch with a B condition)");
   launch_kernel(sampler_step_kernel, dim3(ew_grid(m, 128)), dim3(128), 0, ST(stream), 
       reinterpret_cast<const float4*>(eps), reinterpret_cast<float4*>(latents),
       reinterpret_cast<float4*>(x0), reinterpret_cast<const float4*>(rgb_latents),
       reinterpret_cast<uint4*>(unet_in), m, coef, step_ptr, nsteps, self_cond, mask,
-      reinterpret_cast<const float4*>(known), reinterpret_cast<const float4*>(noise), sigma);
+      reinterpret_cast<const float4*>(known), reinterpret_cast<const float4*>(noise), sigma, prediction_type, clip,
+      clip_range, cfg, guidance);
   return check_launch("sampler_step_kernel");
+}
+
+extern "C" int ldmseg_noise_mix(const float* x, const float* noise, const int64_t* timesteps_dev,
+                                const float* alphas_cumprod_dev, int nb, int64_t per_sample, float scale, int mode,
+                                float* out, void* unet_in, int hw, int cpad, void* stream) {
+  LDM_REQUIRE(x && noise && timesteps_dev && alphas_cumprod_dev && out, "noise_mix: null pointer");
+  LDM_REQUIRE(mode == 0 || mode == 1, "noise_mix: mode must be 0 (add_noise) or 1 (remove_noise)");
+  LDM_REQUIRE(!unet_in || (mode == 0 && hw > 0 && per_sample % hw == 0 && per_sample / hw <= cpad),
+              "noise_mix: unet_in needs mode 0 and per_sample = channels * hw with channels <= cpad");
+  const long long total = static_cast<long long>(nb) * per_sample;
+  if (total == 0) return 0;
+  launch_kernel(noise_mix_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), x, noise,
+                reinterpret_cast<const long long*>(timesteps_dev), alphas_cumprod_dev, nb,
+                static_cast<long long>(per_sample), scale, mode, out, reinterpret_cast<__nv_bfloat16*>(unet_in), hw, cpad);
+  return check_launch("noise_mix_kernel");
 }
 
 extern "C" int ldmseg_advance_step(int* step_ptr, void* stream) {

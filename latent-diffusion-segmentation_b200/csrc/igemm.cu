@@ -49,12 +49,19 @@ struct alignas(64) IgemmKParams {
   const float* bias;
   const float* rowbias;
   int rowbias_ld;
-  const __nv_bfloat16* residual;
+  const void* residual;   // bf16, or f32 when res_f32 (fp32 residual stream)
   int res_ld;
+  int res_f32;
   void* out;
   int out_ld;
   int out_f32;
+  __nv_bfloat16* out2;    // optional bf16 shadow of an f32 output (the copy TMA consumers read)
+  int out2_ld;
   int act;
+  int a_stride;           // 1, or 2: stride-2 conv through the TMA traversal stride (input is 2h x 2w)
+  int a_pad;              // zero padding before (top / left): tap (ky, kx) reads input (s*y + ky - pad, s*x + kx - pad)
+  const uint8_t* next_w;  // weights of the NEXT igemm launch on the stream: pulled into L2 once this CTA's own
+  unsigned long long next_w_bytes;  // operand loads are all in flight (weight streaming at small batch)
   int split_k;
   float* workspace;   // split-K partial tiles: [tile][split][128][BN] f32
   int* counters;
@@ -134,11 +141,12 @@ __device__ __forceinline__ float2 fast_gelu2(float2 x) {
 // Epilogue arguments held in registers (reading them through the parameter block from inside the loops
 // made every access a load the compiler had to repeat after each global store).
 struct EpiArgs {
-  int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw, vec_ok;
+  int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw, vec_ok, res_f32, out2_ld;
   const float* bias;
   const float* rowbias;
-  const __nv_bfloat16* residual;
+  const void* residual;
   void* out;
+  __nv_bfloat16* out2;
   float* stats;
 };
 
@@ -193,14 +201,26 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
       return;
     } else {
       if (p.residual != nullptr && row_ok) {
-        const __nv_bfloat16* rp = p.residual + static_cast<size_t>(m) * p.res_ld + col0;
-        uint32_t r0[8], r1[8];
-        ldg256_nc(rp, r0);
-        ldg256_nc(rp + 16, r1);
+        if (p.res_f32) {   // fp32 residual stream
+          const float* rp = reinterpret_cast<const float*>(p.residual) + static_cast<size_t>(m) * p.res_ld + col0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 a = unpack_bf16x2(r0[i]), b = unpack_bf16x2(r1[i]);
-          v[2 * i] += a.x; v[2 * i + 1] += a.y; v[16 + 2 * i] += b.x; v[17 + 2 * i] += b.y;
+          for (int j = 0; j < 4; ++j) {
+            uint32_t r[8];
+            ldg256_nc(rp + 8 * j, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] += __uint_as_float(r[i]);
+          }
+        } else {
+          const __nv_bfloat16* rp =
+              reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<size_t>(m) * p.res_ld + col0;
+          uint32_t r0[8], r1[8];
+          ldg256_nc(rp, r0);
+          ldg256_nc(rp + 16, r1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 a = unpack_bf16x2(r0[i]), b = unpack_bf16x2(r1[i]);
+            v[2 * i] += a.x; v[2 * i + 1] += a.y; v[16 + 2 * i] += b.x; v[17 + 2 * i] += b.y;
+          }
         }
       }
       if (p.act == LDMSEG_ACT_SILU) {
@@ -212,6 +232,17 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
           float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) stg256(op + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&v[8 * j]));
+          if (p.out2 != nullptr) {   // bf16 shadow for the consumers that read this tensor through TMA
+            uint32_t o0[8], o1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o0[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              o1[i] = pack_bf16x2(v[16 + 2 * i], v[17 + 2 * i]);
+            }
+            __nv_bfloat16* o2 = p.out2 + static_cast<size_t>(m) * p.out2_ld + col0;
+            stg256(o2, o0);
+            stg256(o2 + 16, o1);
+          }
         }
       } else {
         uint32_t o0[8], o1[8];
@@ -248,10 +279,14 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
       float x = tmp[i];
       if (p.bias != nullptr) x += __ldg(p.bias + col);
       if (rb != nullptr) x += __ldg(rb + col);
-      if (p.residual != nullptr) x += __bfloat162float(p.residual[static_cast<size_t>(m) * p.res_ld + col]);
+      if (p.residual != nullptr)
+        x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[static_cast<size_t>(m) * p.res_ld + col]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                             p.residual)[static_cast<size_t>(m) * p.res_ld + col]);
       if (p.act == LDMSEG_ACT_SILU) x = fast_silu(x);
       if (p.out_f32) {
         reinterpret_cast<float*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = x;
+        if (p.out2 != nullptr) p.out2[static_cast<size_t>(m) * p.out2_ld + col] = __float2bfloat16(x);
       } else {
         const __nv_bfloat16 o = __float2bfloat16(x);
         reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = o;
@@ -447,8 +482,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         const int n_tile = tile - m_unit * p.num_n_tiles;
         const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
         const int m0 = m_tile * BM;
-        const int x0 = m0 % p.W;
-        const int y0 = (m0 / p.W) % p.H;
+        const int x0 = (m0 % p.W) * p.a_stride;
+        const int y0 = ((m0 / p.W) % p.H) * p.a_stride;
         const int b0 = m0 / p.HW;
         const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
         const int kb_end =
@@ -473,8 +508,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           }
           int dx = 0, dy = 0;
           if (p.seg_taps[seg] == 9) {
-            dy = tap / 3 - 1;
-            dx = tap - (tap / 3) * 3 - 1;
+            dy = tap / 3 - p.a_pad;
+            dx = tap - (tap / 3) * 3 - p.a_pad;
           }
           if (!skip_a) {
             if constexpr (PAIR)
@@ -496,6 +531,18 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
               ++seg;
             }
           }
+        }
+      }
+      // All of this CTA's operand loads are in flight.  From here to the end of the launch (MMA tail, split-K
+      // exchange, epilogue, drain, the norm kernel in between, the successor's prologue) DRAM would idle: pull this
+      // CTA's slice of the NEXT igemm launch's weights into L2 (a hint: no completion, no dependency).
+      if (p.next_w != nullptr) {
+        constexpr unsigned long long kPiece = 8192;
+        const unsigned long long pieces = (p.next_w_bytes + kPiece - 1) / kPiece;
+        for (unsigned long long i = blockIdx.x; i < pieces; i += gridDim.x) {
+          const unsigned long long off = i * kPiece;
+          const unsigned long long len = p.next_w_bytes - off < kPiece ? p.next_w_bytes - off : kPiece;
+          bulk_prefetch_l2(p.next_w + off, static_cast<uint32_t>(len & ~15ull));
         }
       }
     }
@@ -562,6 +609,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     ea.rowbias_ld = p.rowbias_ld; ea.act = p.act; ea.out_f32 = p.out_f32; ea.split_k = p.split_k;
     ea.stats_hw = p.stats_hw; ea.vec_ok = p.vec_ok; ea.bias = p.bias; ea.rowbias = p.rowbias;
     ea.residual = p.residual; ea.out = p.out; ea.stats = p.stats;
+    ea.res_f32 = p.res_f32; ea.out2 = p.out2; ea.out2_ld = p.out2_ld;
     const uint32_t tmem_empty0 = PAIR ? map_to_cta(&tmem_empty[0], 0) : 0u;   // the leader's barrier
     auto release_acc = [&](int acc) {
       if constexpr (PAIR) mbar_arrive_cluster(tmem_empty0 + acc * 8);
@@ -652,6 +700,9 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
   const int m = static_cast<int>(idx / ncols);
   const int n = static_cast<int>(idx - static_cast<long long>(m) * ncols);
   const int x = m % p.w, y = (m / p.w) % p.h, b = m / HW;
+  const int stride = p.conv_stride == 2 ? 2 : 1;
+  const int pad = p.conv_stride == 2 ? p.conv_pad : 1;
+  const int hin = p.h * stride, win = p.w * stride;
   const __nv_bfloat16* wbase = reinterpret_cast<const __nv_bfloat16*>(p.weight);
   const int kblocks = p.ktot / 64;
   auto wat = [&](int k) -> float {
@@ -670,13 +721,13 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
     for (int tap = 0; tap < p.seg_taps[s]; ++tap) {
       int dy = 0, dx = 0;
       if (p.seg_taps[s] == 9) {
-        dy = tap / 3 - 1;
-        dx = tap % 3 - 1;
+        dy = tap / 3 - pad;
+        dx = tap % 3 - pad;
       }
-      const int yy = y + dy, xx = x + dx;
-      if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
+      const int yy = y * stride + dy, xx = x * stride + dx;
+      if (yy >= 0 && yy < hin && xx >= 0 && xx < win) {
         const __nv_bfloat16* arow =
-            a + (static_cast<size_t>(b) * HW + static_cast<size_t>(yy) * p.w + xx) * C;
+            a + (static_cast<size_t>(b) * hin * win + static_cast<size_t>(yy) * win + xx) * C;
         for (int c = 0; c < C; ++c)
           acc += __bfloat162float(arow[c]) * wat(koff + c);
       }
@@ -699,11 +750,14 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
     return;
   }
   if (p.residual)
-    acc += __bfloat162float(
-        reinterpret_cast<const __nv_bfloat16*>(p.residual)[static_cast<size_t>(m) * p.res_ld + n]);
+    acc += p.residual_f32
+               ? reinterpret_cast<const float*>(p.residual)[static_cast<size_t>(m) * p.res_ld + n]
+               : __bfloat162float(
+                     reinterpret_cast<const __nv_bfloat16*>(p.residual)[static_cast<size_t>(m) * p.res_ld + n]);
   if (p.act == LDMSEG_ACT_SILU) acc = silu_f(acc);
   if (p.out_dtype == LDMSEG_OUT_F32) {
     reinterpret_cast<float*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] = acc;
+    if (p.out2) reinterpret_cast<__nv_bfloat16*>(p.out2)[static_cast<size_t>(m) * p.out2_ld + n] = __float2bfloat16(acc);
   } else {
     const __nv_bfloat16 o = __float2bfloat16(acc);
     reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] = o;
@@ -759,6 +813,16 @@ static int validate(const ldmseg_igemm_params* p) {
     LDM_REQUIRE(p->out_ld % 4 == 0, "igemm: f32 out_ld must be a multiple of 4");
   if (p->residual) LDM_REQUIRE(p->res_ld % 4 == 0, "igemm: res_ld must be a multiple of 4");
   LDM_REQUIRE(p->n % 4 == 0, "igemm: n must be a multiple of 4 (got %d)", p->n);
+  LDM_REQUIRE(p->conv_stride == 0 || p->conv_stride == 1 || p->conv_stride == 2, "igemm: conv_stride must be 1 or 2");
+  if (p->conv_stride == 2) {
+    LDM_REQUIRE(p->conv_pad == 0 || p->conv_pad == 1, "igemm: stride-2 conv_pad must be 0 or 1");
+    for (int s = 0; s < p->nseg; ++s) LDM_REQUIRE(p->seg_taps[s] == 9, "igemm: stride 2 is defined for 3x3 segments only");
+  }
+  if (p->out2) {
+    LDM_REQUIRE(p->out_dtype == LDMSEG_OUT_F32 && p->act != LDMSEG_ACT_GEGLU, "igemm: out2 (bf16 shadow) needs an f32 out");
+    LDM_REQUIRE(p->out2_ld % 4 == 0, "igemm: out2_ld must be a multiple of 4");
+  }
+  if (p->next_weight) LDM_REQUIRE((reinterpret_cast<uintptr_t>(p->next_weight) & 15) == 0, "igemm: next_weight misaligned");
   if (p->rowbias) LDM_REQUIRE(p->rowbias_ld % 4 == 0, "igemm: rowbias_ld must be a multiple of 4");
   if (p->stats) {
     LDM_REQUIRE((p->stats_hw > 0 ? p->stats_hw : hw) % 32 == 0, "igemm: fused statistics need rows per image %% 32 == 0");
@@ -864,14 +928,20 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   uint32_t bw = p->w >= BM ? BM : p->w;
   uint32_t bh = (p->w >= BM) ? 1 : (HW >= BM ? BM / p->w : p->h);
   uint32_t bb = BM / (bw * bh);
+  // stride-2 convs read the 2h x 2w input through the TMA traversal stride: a box of (2 bw) x (2 bh) traversed
+  // elements lands as bw x bh pixels in shared memory -- no im2col buffer
+  const uint32_t cs = p->conv_stride == 2 ? 2 : 1;
   for (int i = 0; i < p->nsrc; ++i) {
     const uint64_t C = p->src_c[i];
-    uint64_t dims[4] = {C, static_cast<uint64_t>(p->w), static_cast<uint64_t>(p->h),
-                        static_cast<uint64_t>(p->nb)};
-    uint64_t strides[3] = {C * 2, C * 2 * p->w, C * 2 * p->w * p->h};
-    uint32_t box[4] = {BK, bw, bh, bb};
-    if (int rc = encode_tmap_bf16(&kp.a_map[i], p->src[i], 4, dims, strides, box)) return rc;
+    const uint64_t win = static_cast<uint64_t>(p->w) * cs, hin = static_cast<uint64_t>(p->h) * cs;
+    uint64_t dims[4] = {C, win, hin, static_cast<uint64_t>(p->nb)};
+    uint64_t strides[3] = {C * 2, C * 2 * win, C * 2 * win * hin};
+    uint32_t box[4] = {BK, bw * cs, bh * cs, bb};
+    uint32_t estr[4] = {1, cs, cs, 1};
+    if (int rc = encode_tmap_bf16(&kp.a_map[i], p->src[i], 4, dims, strides, box, cs == 2 ? estr : nullptr)) return rc;
   }
+  kp.a_stride = static_cast<int>(cs);
+  kp.a_pad = cs == 2 ? p->conv_pad : 1;
   const int m_tiles = (M + BM - 1) / BM;
   int bn = p->block_n;
   if (bn == 0) bn = choose_block_n(m_tiles, p->n, num_sms());
@@ -918,8 +988,22 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   kp.bias = p->bias;
   kp.rowbias = p->rowbias;
   kp.rowbias_ld = p->rowbias_ld;
-  kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
+  kp.residual = p->residual;
   kp.res_ld = p->res_ld;
+  kp.res_f32 = p->residual_f32 ? 1 : 0;
+  kp.out2 = reinterpret_cast<__nv_bfloat16*>(p->out2);
+  kp.out2_ld = p->out2_ld;
+  {
+    static int mode = -1;  // LDMSEG_NEXTW=0 disables the next-launch weight prefetch (A/B timing)
+    if (mode < 0) {
+      const char* e = getenv("LDMSEG_NEXTW");
+      mode = e ? atoi(e) : 1;
+    }
+    if (mode != 0 && p->next_weight != nullptr && p->next_weight_bytes >= 16) {
+      kp.next_w = reinterpret_cast<const uint8_t*>(p->next_weight);
+      kp.next_w_bytes = static_cast<unsigned long long>(p->next_weight_bytes);
+    }
+  }
   kp.out = p->out;
   kp.out_ld = p->out_ld;
   kp.out_f32 = p->out_dtype == LDMSEG_OUT_F32;
@@ -947,13 +1031,18 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
       const char* e = getenv("LDMSEG_IGEMM_PREFETCH");
       mode = e ? atoi(e) : 1;
     }
-    kp.prefetch_b = mode != 0 && !(g_debug & 24);
+    // only for operands that nothing on the stream writes (real weights): a B operand produced by an earlier
+    // launch (the VAE attention's K / V^T) must not be read before the grid-dependency wait
+    kp.prefetch_b = mode != 0 && p->weight_static != 0 && !(g_debug & 24);
   }
   {
     const size_t esz = kp.out_f32 ? 4 : 2;
     bool ok = (reinterpret_cast<uintptr_t>(p->out) & 31) == 0 && (static_cast<size_t>(p->out_ld) * esz) % 32 == 0;
     if (p->residual)
-      ok = ok && (reinterpret_cast<uintptr_t>(p->residual) & 31) == 0 && (static_cast<size_t>(p->res_ld) * 2) % 32 == 0;
+      ok = ok && (reinterpret_cast<uintptr_t>(p->residual) & 31) == 0 &&
+           (static_cast<size_t>(p->res_ld) * (p->residual_f32 ? 4 : 2)) % 32 == 0;
+    if (p->out2)
+      ok = ok && (reinterpret_cast<uintptr_t>(p->out2) & 31) == 0 && (static_cast<size_t>(p->out2_ld) * 2) % 32 == 0;
     if (p->bias) ok = ok && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
     if (p->rowbias) ok = ok && (reinterpret_cast<uintptr_t>(p->rowbias) & 15) == 0 && p->rowbias_ld % 4 == 0;
     kp.vec_ok = ok ? 1 : 0;

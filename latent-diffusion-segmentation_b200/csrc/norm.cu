@@ -140,8 +140,9 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ s0, int c0,
 }
 
 // ---- LayerNorm over channels, one warp per row ---------------------------------------------
-template <int MAXV>
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ src, int rows, int c,
+// SRC_F32: the row is f32 (fp32 residual stream) instead of bf16.
+template <int MAXV, bool SRC_F32>
+__global__ void layernorm_kernel(const void* __restrict__ srcv, int rows, int c,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, int silu, __nv_bfloat16* __restrict__ out) {
   pdl_sync();
@@ -149,14 +150,23 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ src, int rows
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = c >> 3;
-  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(row) * c);
   float f[MAXV][8];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + i * 32;
     if (v < nv) {
-      unpack8(__ldg(s + v), f[i]);
+      if constexpr (SRC_F32) {
+        const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(srcv) +
+                                                          static_cast<size_t>(row) * c);
+        const float4 a = __ldg(s + 2 * v), b = __ldg(s + 2 * v + 1);
+        f[i][0] = a.x; f[i][1] = a.y; f[i][2] = a.z; f[i][3] = a.w;
+        f[i][4] = b.x; f[i][5] = b.y; f[i][6] = b.z; f[i][7] = b.w;
+      } else {
+        const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(srcv) +
+                                                        static_cast<size_t>(row) * c);
+        unpack8(__ldg(s + v), f[i]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += f[i][j];
     }
@@ -363,22 +373,32 @@ extern "C" int ldmseg_groupnorm(const void* src0, int c0, const void* src1, int 
   return check_launch("gn_apply_kernel");
 }
 
-extern "C" int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma,
-                                const float* beta, float eps, int silu, void* out, void* stream) {
+template <bool SRC_F32>
+static int layernorm_launch(const void* src, int rows, int c, const float* gamma, const float* beta, float eps,
+                            int silu, void* out, void* stream) {
   LDM_REQUIRE(src && out && gamma && beta, "layernorm: null pointer");
   LDM_REQUIRE(c % 8 == 0 && c <= 2048, "layernorm: c must be a multiple of 8 and <= 2048");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (c <= 512)
-    launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(wpb * 32), 0, st, s, rows, c, gamma, beta, eps, silu, o);
+    launch_kernel(layernorm_kernel<2, SRC_F32>, dim3(grid), dim3(wpb * 32), 0, st, src, rows, c, gamma, beta, eps, silu, o);
   else if (c <= 1280)
-    launch_kernel(layernorm_kernel<5>, dim3(grid), dim3(wpb * 32), 0, st, s, rows, c, gamma, beta, eps, silu, o);
+    launch_kernel(layernorm_kernel<5, SRC_F32>, dim3(grid), dim3(wpb * 32), 0, st, src, rows, c, gamma, beta, eps, silu, o);
   else
-    launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, st, s, rows, c, gamma, beta, eps, silu, o);
+    launch_kernel(layernorm_kernel<8, SRC_F32>, dim3(grid), dim3(wpb * 32), 0, st, src, rows, c, gamma, beta, eps, silu, o);
   return check_launch("layernorm_kernel");
+}
+
+extern "C" int ldmseg_layernorm(const void* src, int rows, int c, const float* gamma,
+                                const float* beta, float eps, int silu, void* out, void* stream) {
+  return layernorm_launch<false>(src, rows, c, gamma, beta, eps, silu, out, stream);
+}
+
+extern "C" int ldmseg_layernorm_f32(const void* src, int rows, int c, const float* gamma,
+                                    const float* beta, float eps, int silu, void* out, void* stream) {
+  return layernorm_launch<true>(src, rows, c, gamma, beta, eps, silu, out, stream);
 }
 
 extern "C" int ldmseg_convt_shuffle_ln(const void* src, int nb, int h, int w, int c,

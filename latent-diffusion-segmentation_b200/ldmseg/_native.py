@@ -30,6 +30,8 @@ EXPORTS = [
     "ldmseg_small_linear", "ldmseg_convt_shuffle_ln", "ldmseg_bilinear2x_to_nchw",
     "ldmseg_bilinear2x_argmax", "ldmseg_select_row", "ldmseg_ddim_step_indexed", "ldmseg_softmax_rows", "ldmseg_nchw_f32_to_nhwc",
     "ldmseg_groupnorm_apply_cs", "ldmseg_set_pdl", "ldmseg_set_debug",
+    "ldmseg_groupnorm_apply_cs_f32", "ldmseg_layernorm_f32", "ldmseg_noise_mix", "ldmseg_cross_attention",
+    "ldmseg_panoptic_resample", "ldmseg_panoptic_filter",
 ]
 
 
@@ -64,6 +66,14 @@ class IgemmParams(C.Structure):
         ("weight_tiled", C.c_int),
         ("pdl", C.c_int),
         ("pair", C.c_int),
+        ("weight_static", C.c_int),
+        ("next_weight", C.c_void_p),
+        ("next_weight_bytes", C.c_longlong),
+        ("residual_f32", C.c_int),
+        ("out2", C.c_void_p),
+        ("out2_ld", C.c_int),
+        ("conv_stride", C.c_int),
+        ("conv_pad", C.c_int),
     ]
 
 
@@ -95,6 +105,9 @@ def load() -> C.CDLL:
         "ldmseg_layernorm": [vp, i32, i32, vp, vp, f32, i32, vp, vp],
         "ldmseg_attention": [vp, i32, i32, i32, i32, vp, vp],
         "ldmseg_attention_simple": [vp, i32, i32, i32, i32, vp, vp],
+        "ldmseg_cross_attention": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
+        "ldmseg_panoptic_resample": [vp, i32, i32, i32, i32, vp, i32, i32, f32, i32, vp, vp, vp, vp],
+        "ldmseg_panoptic_filter": [vp, i32, vp, i32, i32, vp, vp, i32, C.c_double, i32, vp, vp, vp],
         "ldmseg_geglu": [vp, i32, i32, vp, vp],
         "ldmseg_upsample2x": [vp, i32, i32, i32, i32, vp, vp],
         "ldmseg_im2col_s2": [vp, i32, i32, i32, i32, i32, vp, vp],
@@ -103,7 +116,10 @@ def load() -> C.CDLL:
         "ldmseg_nhwc_bf16_to_nchw": [vp, i32, i32, i32, i32, f32, vp, vp],
         "ldmseg_nchw_f32_to_nhwc": [vp, i32, i32, i32, i32, f32, vp, vp],
         "ldmseg_ddim_step": [vp, vp, i64, f32, f32, i32, i32, f32, i32, f32, vp, vp, vp, vp],
-        "ldmseg_sampler_step": [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, vp],
+        "ldmseg_sampler_step": [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, f32, i32, f32, vp],
+        "ldmseg_noise_mix": [vp, vp, vp, vp, i32, i64, f32, i32, vp, vp, i32, i32, vp],
+        "ldmseg_groupnorm_apply_cs_f32": [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, vp, vp],
+        "ldmseg_layernorm_f32": [vp, i32, i32, vp, vp, f32, i32, vp, vp],
         "ldmseg_advance_step": [vp, vp],
         "ldmseg_timestep_sinusoid": [vp, i32, i32, i32, f32, vp, vp],
         "ldmseg_small_linear": [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp],
@@ -160,7 +176,8 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       block_n: int = 0, split_k: int = 0, workspace: Optional[torch.Tensor] = None,
                       counters: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
                       stats_hw: int = 0, pdl: bool = False, weight_tiled: bool = False,
-                      pair: bool = False) -> IgemmParams:
+                      pair: bool = False, weight_static: bool = False, out2: Optional[torch.Tensor] = None,
+                      conv_stride: int = 1, conv_pad: int = 1) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -196,6 +213,14 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.weight_tiled = int(weight_tiled)
     p.pdl = int(pdl)
     p.pair = int(pair)
+    p.weight_static = int(weight_static)
+    p.next_weight = None
+    p.next_weight_bytes = 0
+    p.residual_f32 = int(residual is not None and residual.dtype == torch.float32)
+    p.out2 = _ptr(out2)
+    p.out2_ld = out2.shape[1] if out2 is not None else 0
+    p.conv_stride = conv_stride
+    p.conv_pad = conv_pad
     return p
 
 
@@ -212,14 +237,20 @@ def groupnorm(src0, c0, src1, c1, nb, hw, groups, gamma, beta, eps, silu, out, s
 
 
 def layernorm(src, rows, c, gamma, beta, eps, silu, out) -> None:
-    _check(load().ldmseg_layernorm(_ptr(src), rows, c, _ptr(gamma), _ptr(beta), eps, int(silu),
-                                   _ptr(out), _stream()), "ldmseg_layernorm")
+    fn = load().ldmseg_layernorm_f32 if src.dtype == torch.float32 else load().ldmseg_layernorm
+    _check(fn(_ptr(src), rows, c, _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(out), _stream()),
+           "ldmseg_layernorm")
 
 
 def attention(qkv, nb, ntok, heads, d, out, simple: bool = False) -> None:
     lib = load()
     fn = lib.ldmseg_attention_simple if simple else lib.ldmseg_attention
     _check(fn(_ptr(qkv), nb, ntok, heads, d, _ptr(out), _stream()), "ldmseg_attention")
+
+
+def cross_attention(q, kv, nb, ntok_q, ntok_kv, heads, d, out) -> None:
+    _check(load().ldmseg_cross_attention(_ptr(q), _ptr(kv), nb, ntok_q, ntok_kv, heads, d, _ptr(out), _stream()),
+           "ldmseg_cross_attention")
 
 
 def geglu(x, rows, c, out) -> None:
@@ -258,11 +289,20 @@ def ddim_step(model_out, sample, alpha_t, alpha_prev, ptype, clip, clip_range, u
 
 
 def sampler_step(eps, latents, x0, rgb, unet_in, m, coef, step_ptr, nsteps, self_cond, mask=None,
-                 known=None, noise=None, sigma=None) -> None:
+                 known=None, noise=None, sigma=None, ptype: int = 0, clip: bool = False,
+                 clip_range: float = 1.0, cfg: bool = False, guidance: float = 1.0) -> None:
     _check(load().ldmseg_sampler_step(_ptr(eps), _ptr(latents), _ptr(x0), _ptr(rgb), _ptr(unet_in), m,
                                       _ptr(coef), _ptr(step_ptr), nsteps, int(self_cond), _ptr(mask),
-                                      _ptr(known), _ptr(noise), _ptr(sigma), _stream()),
+                                      _ptr(known), _ptr(noise), _ptr(sigma), ptype, int(clip), clip_range,
+                                      int(cfg), guidance, _stream()),
            "ldmseg_sampler_step")
+
+
+def noise_mix(x, noise, timesteps_dev, acp_dev, nb, per_sample, scale, mode, out, unet_in=None, hw=0,
+              cpad=0) -> None:
+    _check(load().ldmseg_noise_mix(_ptr(x), _ptr(noise), _ptr(timesteps_dev), _ptr(acp_dev), nb, per_sample,
+                                   scale, mode, _ptr(out), _ptr(unet_in), hw, cpad, _stream()),
+           "ldmseg_noise_mix")
 
 
 def advance_step(step_ptr) -> None:
@@ -296,6 +336,20 @@ def bilinear2x_argmax(src, nb, h, w, c, ld, ids, maxprob=None) -> None:
            "ldmseg_bilinear2x_argmax")
 
 
+def panoptic_resample(logits, nb, s, c, ld, geom, max_hw, out_stride, mask_th, threshold_output, pred, area,
+                      orig_area) -> None:
+    _check(load().ldmseg_panoptic_resample(_ptr(logits), nb, s, c, ld, _ptr(geom), max_hw, out_stride, mask_th,
+                                           int(threshold_output), _ptr(pred), _ptr(area), _ptr(orig_area),
+                                           _stream()), "ldmseg_panoptic_resample")
+
+
+def panoptic_filter(pred, nb, geom, max_hw, out_stride, area, orig_area, count_th, overlap_th, ignore_label, ids,
+                    keep) -> None:
+    _check(load().ldmseg_panoptic_filter(_ptr(pred), nb, _ptr(geom), max_hw, out_stride, _ptr(area),
+                                         _ptr(orig_area), count_th, overlap_th, ignore_label, _ptr(ids),
+                                         _ptr(keep), _stream()), "ldmseg_panoptic_filter")
+
+
 def select_row(table, ncols, step_ptr, nb, dst) -> None:
     _check(load().ldmseg_select_row(_ptr(table), ncols, _ptr(step_ptr), nb, _ptr(dst), _stream()),
            "ldmseg_select_row")
@@ -320,9 +374,11 @@ def nchw_f32_to_nhwc(src, nb, c, hw, ld, scale, out) -> None:
 
 
 def groupnorm_apply_cs(src0, c0, cs0, src1, c1, cs1, nb, hw, groups, gamma, beta, eps, silu, out) -> None:
-    _check(load().ldmseg_groupnorm_apply_cs(_ptr(src0), c0, _ptr(cs0), _ptr(src1), c1, _ptr(cs1), nb, hw, groups,
-                                            _ptr(gamma), _ptr(beta), eps, int(silu), _ptr(out), _stream()),
-           "ldmseg_groupnorm_apply_cs")
+    f32 = src0.dtype == torch.float32
+    assert src1 is None or (src1.dtype == torch.float32) == f32, "GroupNorm sources must share a dtype"
+    fn = load().ldmseg_groupnorm_apply_cs_f32 if f32 else load().ldmseg_groupnorm_apply_cs
+    _check(fn(_ptr(src0), c0, _ptr(cs0), _ptr(src1), c1, _ptr(cs1), nb, hw, groups, _ptr(gamma), _ptr(beta), eps,
+              int(silu), _ptr(out), _stream()), "ldmseg_groupnorm_apply_cs")
 
 
 def set_pdl(enable: bool) -> bool:

@@ -19,6 +19,14 @@ CYC_PER_TMA_ROW = 2.17
 USE_PDL = os.environ.get("LDMSEG_PDL", "1") != "0"
 FUSE_GN_STATS = os.environ.get("LDMSEG_FUSE_GN_STATS", "1") != "0"
 USE_PAIR = os.environ.get("LDMSEG_PAIR", "1") != "0"     # CTA pairs (tcgen05 cta_group::2) where the model prefers them
+# stride-2 convolutions read their input through the TMA traversal stride (no im2col buffer); 0 = im2col + GEMM
+USE_S2_TMA = os.environ.get("LDMSEG_S2_TMA", "1") != "0"
+# fp32 residual / skip stream (SURVEY.md §7 hard part 3): every tensor that is added back later (resnet outputs,
+# transformer hidden states) is kept in f32, with a bf16 shadow only where a later launch reads it through TMA
+RESID_F32 = os.environ.get("LDMSEG_RESID_F32", "0") != "0"
+# each igemm launch pulls the NEXT launch's weights into L2 while its own tail runs (weight streaming at small
+# batch); only below this many output rows per forward level-0 launch (large batches are compute-bound)
+NEXTW_MAX_ROWS = int(os.environ.get("LDMSEG_NEXTW_MAX_ROWS", "8192"))
 
 
 USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
@@ -104,6 +112,16 @@ class WeightsBase:
         self.L: Dict[str, _Layer] = {}
         self.norms: Dict[str, Tuple[torch.Tensor, torch.Tensor, float]] = {}
         self.groups = 32
+        self._shared: Dict[str, torch.Tensor] = {}
+
+    def shared(self, name: str, numel: int, dtype) -> torch.Tensor:
+        """Scratch shared by every plan of this engine (plans run one at a time on one stream): split-K
+        workspace and tile counters.  Grows on demand."""
+        t = self._shared.get(name)
+        if t is None or t.numel() < numel:
+            t = torch.zeros(numel, device=self.device, dtype=dtype)
+            self._shared[name] = t
+        return t
 
     def _dev(self, t, dtype=None):
         return t.detach().to(device=self.device, dtype=dtype or t.dtype).contiguous()
@@ -112,6 +130,7 @@ class WeightsBase:
         extra.setdefault("ktot", packed_f32.shape[1])
         extra.setdefault("tiled", True)
         extra.setdefault("name", name)
+        extra.setdefault("static", True)      # a real parameter: nothing on the stream writes it
         self.L[name] = _Layer(self._dev(pk.tile_pack(packed_f32), torch.bfloat16),
                               None if bias is None else self._dev(bias.float()), n, **extra)
 
@@ -125,10 +144,25 @@ class WeightsBase:
         self._gemm(name + ".conv1", pk.pack_conv3x3(r.conv1.weight), r.conv1.bias, r.out_channels)
         w2 = pk.pack_conv3x3(r.conv2.weight)
         b2 = r.conv2.bias.detach().float().clone()
-        if r.conv_shortcut is not None:
+        has_sc = r.conv_shortcut is not None
+        if has_sc:
             w2 = torch.cat([w2, pk.split_linear_k(r.conv_shortcut.weight, src_split)], dim=1)
             b2 = b2 + r.conv_shortcut.bias.detach().float()
-        self._gemm(name + ".conv2", w2, b2, r.out_channels)
+        self._gemm(name + ".conv2", w2, b2, r.out_channels, shortcut=has_sc)
+
+    def _conv_s2(self, name, conv):
+        """3x3 stride-2 convolution: per-tap packing for the TMA-strided kernel, im2col packing otherwise."""
+        w = conv.weight
+        if USE_S2_TMA:
+            c = w.shape[1]
+            if c % 8:
+                cp = (c + 15) // 16 * 16
+                wp = torch.zeros(w.shape[0], cp, 3, 3, device=w.device)
+                wp[:, :c] = w.detach().float()
+                w = wp
+            self._gemm(name, pk.pack_conv3x3(w), conv.bias, conv.out_channels, s2_tma=True)
+        else:
+            self._gemm(name, pk.pack_conv3x3_im2col(w), conv.bias, conv.out_channels, s2_tma=False)
 
 
 class PlanBase:
@@ -138,15 +172,19 @@ class PlanBase:
     an igemm of this plan: `_gn` then assigns that producer a slice of `stats_arena` (per-image,
     per-channel sum / sum of squares, zeroed once per run) and emits a single apply kernel."""
 
-    def __init__(self, W: WeightsBase, nb: int):
+    def __init__(self, W: WeightsBase, nb: int, allow_split: bool = True):
         self.W, self.nb = W, nb
+        self.allow_split = allow_split   # False: no launch of this plan waits for sibling CTAs (side-stream use)
         self.device = W.device
         self.ops: List[Callable[[], None]] = []
         self.tags: List[str] = []            # one per op: "<family>:<rows>:<layer>" (profiling / ablation only)
         self.n_launch = 0
         self._keep: list = []
-        self.ws = torch.zeros(16 * 1024 * 1024, device=self.device, dtype=torch.float32)  # split-K partials
-        self.counters = torch.zeros(8192, device=self.device, dtype=torch.int32)
+        self.ws = W.shared("splitk_ws", 16 * 1024 * 1024, torch.float32)   # split-K partials (self-cleaning)
+        self.counters = W.shared("splitk_counters", 8192, torch.int32)
+        self.resid_f32 = RESID_F32
+        self._f32: Dict[int, torch.Tensor] = {}     # bf16 handle ptr -> f32 tensor of the residual stream
+        self._igemm_params: list = []
         self.gn_stats = torch.zeros(nb * 64 * 2, device=self.device, dtype=torch.float32)
         self.stats_arena = torch.zeros(nb * 512 * 1024, device=self.device, dtype=torch.float32)
         self._arena_used = 0
@@ -168,25 +206,71 @@ class PlanBase:
         self.n_launch += launches
 
     def _gemm(self, layer: _Layer, srcs, src_c, nb, h, w, segs, out, *, rowbias=None, residual=None,
-              act=nat.ACT_NONE, out_ld=None, bias="layer", allow_split=True):
+              act=nat.ACT_NONE, out_ld=None, bias="layer", allow_split=True, stream=False, shadow=True,
+              conv_stride=1, conv_pad=1):
+        """Append one igemm launch.  `stream=True` marks `out` as a tensor of the residual stream: under
+        RESID_F32 it is written as f32 (+ a bf16 shadow in `out` when `shadow`), and later `residual=` /
+        GroupNorm / LayerNorm reads of `out` use the f32 copy."""
         num_kb = sum(taps * ((src_c[s] + 63) // 64) for s, taps in segs)
         m = nb * h * w
         tiled = bool(layer.extra.get("tiled", False))
+        allow_split = allow_split and self.allow_split
         bn, split, pair = choose_tiling(m, layer.n, num_kb, allow_split=allow_split, allow_pair=USE_PAIR and tiled)
         tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
         if split > 1 and tiles * split * 128 * bn > self.ws.numel():
             bn, split, pair = choose_tiling(m, layer.n, num_kb, allow_split=False, allow_pair=USE_PAIR and tiled)
-        p = nat.make_igemm_params(srcs, src_c, nb, h, w, segs, layer.w, layer.n, out,
-                                  out_ld if out_ld is not None else out.shape[1],
+        out_main, out2 = out, None
+        if stream and self.resid_f32 and out.dtype == torch.bfloat16:
+            f = self._buf(out.shape[0], out.shape[1], torch.float32)
+            self._f32[out.data_ptr()] = f
+            out_main, out2 = f, (out if shadow else None)
+        if residual is not None:
+            residual = self._f32.get(residual.data_ptr(), residual)
+        p = nat.make_igemm_params(srcs, src_c, nb, h, w, segs, layer.w, layer.n, out_main,
+                                  out_ld if out_ld is not None else out_main.shape[1],
                                   bias=layer.bias if bias == "layer" else bias,
                                   rowbias=rowbias, rowbias_ld=self.rowbias_ld if rowbias is not None else 0,
                                   residual=residual, res_ld=residual.shape[1] if residual is not None else 0,
                                   act=act, block_n=bn, split_k=split, workspace=self.ws, counters=self.counters,
-                                  pdl=self.pdl, weight_tiled=tiled, pair=pair)
+                                  pdl=self.pdl, weight_tiled=tiled, pair=pair,
+                                  weight_static=bool(layer.extra.get("static", False)), out2=out2,
+                                  conv_stride=conv_stride, conv_pad=conv_pad)
         self._keep.append(p)
+        self._igemm_params.append((p, layer, m))
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
         self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}")
+
+    def _down(self, layer: _Layer, x, c, h, pad_lo, act=nat.ACT_NONE):
+        """3x3 stride-2 convolution of x [nb*h*h, c] -> [nb*(h/2)^2, n] (a tensor of the residual stream)."""
+        nb = self.nb
+        ho = h // 2
+        y = self._buf(nb * ho * ho, layer.n)
+        if layer.extra.get("s2_tma", False):
+            self._gemm(layer, [x], [c], nb, ho, ho, [(0, 9)], y, stream=True, conv_stride=2, conv_pad=pad_lo,
+                       act=act)
+        else:
+            col = self._buf(nb * ho * ho, 9 * c)
+            self._op(lambda: nat.im2col_s2(x, nb, h, h, c, pad_lo, col), tag=f"im2col:{nb * h * h}:")
+            self._gemm(layer, [col], [9 * c], 1, 1, nb * ho * ho, [(0, 1)], y, stream=True, act=act)
+        return y
+
+    def link_weight_prefetch(self, max_rows: int = NEXTW_MAX_ROWS) -> None:
+        """Give every igemm launch the weights of the next one (static parameters only) as an L2 prefetch hint;
+        the last launch of the plan points at the first (the plan is replayed step after step).  Skipped for
+        plans whose first launch already has more than `max_rows` output rows (compute-bound batches)."""
+        ps = self._igemm_params
+        if len(ps) < 2 or ps[0][2] > max_rows:
+            return
+        for i, (p, _, _) in enumerate(ps):
+            _, nxt, _ = ps[(i + 1) % len(ps)]
+            if not nxt.extra.get("static", False):
+                continue
+            nbytes = nxt.w.numel() * nxt.w.element_size()
+            if nbytes < (1 << 16) or nbytes > (96 << 20):
+                continue
+            p.next_weight = nxt.w.data_ptr()
+            p.next_weight_bytes = nbytes
 
     def _stats_for(self, src, c, hw) -> Optional[torch.Tensor]:
         """Channel-statistics slice for a GroupNorm source written by an igemm of this plan (or None)."""
@@ -214,6 +298,11 @@ class PlanBase:
         cs0 = self._stats_for(src0, c0, hw)
         cs1 = self._stats_for(src1, c1, hw) if src1 is not None else None
         if cs0 is not None and (src1 is None or cs1 is not None):
+            # fp32 residual stream: read the f32 copies (both sources or neither)
+            f0 = self._f32.get(src0.data_ptr())
+            f1 = self._f32.get(src1.data_ptr()) if src1 is not None else None
+            if f0 is not None and (src1 is None or f1 is not None):
+                src0, src1 = f0, f1
             self._op(lambda: nat.groupnorm_apply_cs(src0, c0, cs0, src1, c1, cs1, nb, hw, groups, g, b, eps, silu,
                                                     out), tag=f"gn:{nb * hw}:{name}")
             return
@@ -223,6 +312,7 @@ class PlanBase:
 
     def _ln(self, name, src, rows, c, out, silu=False):
         g, b, eps = self.W.norms[name]
+        src = self._f32.get(src.data_ptr(), src)
         self._op(lambda: nat.layernorm(src, rows, c, g, b, eps, silu, out), tag=f"ln:{rows}:{name}")
 
     def _resnet(self, name, x, cx, skip, cskip, h, w=None, rowbias=None):
@@ -241,12 +331,15 @@ class PlanBase:
         a2 = self._buf(m, cout)
         self._gn(name + ".norm2", h1, cout, None, 0, hw, True, a2)
         out = self._buf(m, cout)
-        if cin == cout and skip is None:
-            self._gemm(l2, [a2], [cout], nb, h, w, [(0, 9)], out, residual=x)
+        # the 1x1 shortcut rides in conv2 as extra K segments exactly when the layer was packed with it
+        # (WeightsBase._resnet); otherwise the block input is added back as the residual
+        if not l2.extra.get("shortcut", False):
+            assert skip is None and cin == cout, f"{name}: no packed shortcut but cin {cin} != cout {cout}"
+            self._gemm(l2, [a2], [cout], nb, h, w, [(0, 9)], out, residual=x, stream=True)
         elif skip is None:
-            self._gemm(l2, [a2, x], [cout, cx], nb, h, w, [(0, 9), (1, 1)], out)
+            self._gemm(l2, [a2, x], [cout, cx], nb, h, w, [(0, 9), (1, 1)], out, stream=True)
         else:
-            self._gemm(l2, [a2, x, skip], [cout, cx, cskip], nb, h, w, [(0, 9), (1, 1), (2, 1)], out)
+            self._gemm(l2, [a2, x, skip], [cout, cx, cskip], nb, h, w, [(0, 9), (1, 1), (2, 1)], out, stream=True)
         return out
 
     def run(self) -> None:

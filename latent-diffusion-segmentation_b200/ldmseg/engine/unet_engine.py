@@ -16,6 +16,7 @@ shortcuts ride inside conv2), 16 attention launches, 61 GroupNorm, 32 LayerNorm.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -37,7 +38,14 @@ class UNetWeights(WeightsBase):
         self.groups = cfg.norm_num_groups
         self.heads = cfg.attention_head_dim
         self.cin_pad = (self.in_channels + 15) // 16 * 16
+        self.cross_layers = []       # transformer blocks that kept attn2 (none in the released configuration)
+        self.cross_dim = 0
         self._pack(unet)
+        # optional pre-processing of encoder_hidden_states (unet.py:332-336): Linear projection / learned queries
+        hp = getattr(unet, "encoder_hid_proj", None)
+        self.hid_proj = None if hp is None else (self._dev(hp.weight.float()), self._dev(hp.bias.float()))
+        oq = getattr(unet, "object_queries", None)
+        self.object_queries = None if oq is None else self._dev(oq.weight.float())
 
     def _transformer(self, name, t):
         c = t.channels
@@ -45,10 +53,14 @@ class UNetWeights(WeightsBase):
         self._gemm(name + ".proj_in", pk.pack_linear(t.proj_in.weight), t.proj_in.bias, c)
         blk = t.transformer_blocks[0]
         if blk.attn2 is not None:
-            raise NotImplementedError(
-                "ldmseg_b200 UNet engine: cross-attention is not built (LDMSeg's released configuration "
-                "removes it: image_descriptors='remove', ldmseg/models/descriptors.py:94-96). Call "
-                "unet.remove_cross_attention() first.")
+            # conditioned variants (descriptors.py:67-105 other than 'remove'): attn2 reads encoder_hidden_states
+            x = blk.attn2
+            self._norm(name + ".ln2", blk.norm2)
+            self._gemm(name + ".q2", pk.pack_linear(x.to_q.weight), None, c)
+            self._gemm(name + ".kv2", pk.pack_linear(torch.cat([x.to_k.weight, x.to_v.weight], dim=0)), None, 2 * c)
+            self._gemm(name + ".to_out2", pk.pack_linear(x.to_out[0].weight), x.to_out[0].bias, c)
+            self.cross_dim = x.to_k.in_features
+            self.cross_layers.append(name)
         self._norm(name + ".ln1", blk.norm1)
         self._norm(name + ".ln3", blk.norm3)
         a = blk.attn1
@@ -94,8 +106,7 @@ class UNetWeights(WeightsBase):
                 if hasattr(blk, "attentions"):
                     self._transformer(f"down{i}.attn{j}", blk.attentions[j])
             if blk.downsamplers is not None:
-                d = blk.downsamplers[0].conv
-                self._gemm(f"down{i}.down", pk.pack_conv3x3_im2col(d.weight), d.bias, d.out_channels)
+                self._conv_s2(f"down{i}.down", blk.downsamplers[0].conv)
         for j, r in enumerate(unet.mid_block.resnets):
             self._resnet(f"mid.res{j}", r, [r.in_channels])
             reg_temb(f"mid.res{j}", r)
@@ -151,9 +162,17 @@ class UNetPlan(PlanBase):
     Inputs live in `x_in` (bf16 [M, cin_pad]) and `temb` (f32 [nb, temb_total]); the predicted noise
     lands in `eps` (f32 [M, 4], channel-last)."""
 
-    def __init__(self, W: UNetWeights, nb: int, size: int):
+    def __init__(self, W: UNetWeights, nb: int, size: int, ntok_enc: int = 0):
         super().__init__(W, nb)
         self.size = size
+        self.ntok_enc = ntok_enc
+        if W.cross_layers and ntok_enc <= 0:
+            raise RuntimeError("this UNet kept its cross-attention: encoder_hidden_states is required "
+                               "(or call unet.remove_cross_attention(), the released configuration)")
+        self.kv: Dict[str, torch.Tensor] = {}
+        self.kv_ops = []
+        if W.cross_layers:
+            self.enc_in = torch.zeros(nb * ntok_enc, W.cross_dim, device=self.device, dtype=torch.bfloat16)
         m0 = nb * size * size
         self.x_in = torch.zeros(m0, W.cin_pad, device=self.device, dtype=torch.bfloat16)
         self.temb = torch.zeros(nb, W.temb_total, device=self.device, dtype=torch.float32)
@@ -172,7 +191,7 @@ class UNetPlan(PlanBase):
         g = self._buf(m, c)
         self._gn(name + ".norm", x, c, None, 0, hw, False, g)
         t0 = self._buf(m, c)
-        self._gemm(W.L[name + ".proj_in"], [g], [c], 1, 1, m, [(0, 1)], t0)
+        self._gemm(W.L[name + ".proj_in"], [g], [c], 1, 1, m, [(0, 1)], t0, stream=True)
         ln = self._buf(m, c)
         self._ln(name + ".ln1", t0, m, c, ln)
         qkv = self._buf(m, 3 * c)
@@ -180,7 +199,29 @@ class UNetPlan(PlanBase):
         ao = self._buf(m, c)
         self._op(lambda: nat.attention(qkv, nb, hw, heads, d, ao), tag=f"attn:{m}:{name}")
         t1 = self._buf(m, c)
-        self._gemm(W.L[name + ".to_out"], [ao], [c], 1, 1, m, [(0, 1)], t1, residual=t0)
+        self._gemm(W.L[name + ".to_out"], [ao], [c], 1, 1, m, [(0, 1)], t1, residual=t0, stream=True)
+        if name in W.cross_layers:
+            # h = attn2(norm2(h), encoder_hidden_states) + h; K / V of the (step-invariant) encoder states are
+            # produced once per call by `set_encoder_hidden_states`, outside the per-step launch list
+            T = self.ntok_enc
+            kv = self._buf(nb * T, 2 * c)
+            self.kv[name] = kv
+            n_before = len(self.ops)
+            self._gemm(W.L[name + ".kv2"], [self.enc_in], [W.cross_dim], 1, 1, nb * T, [(0, 1)], kv)
+            self.kv_ops.append(self.ops.pop())
+            self.tags.pop()
+            self.n_launch -= 1
+            self._igemm_params.pop()
+            assert len(self.ops) == n_before
+            lnx = self._buf(m, c)
+            self._ln(name + ".ln2", t1, m, c, lnx)
+            qx = self._buf(m, c)
+            self._gemm(W.L[name + ".q2"], [lnx], [c], 1, 1, m, [(0, 1)], qx)
+            ax = self._buf(m, c)
+            self._op(lambda: nat.cross_attention(qx, kv, nb, hw, T, heads, d, ax), tag=f"xattn:{m}:{name}")
+            t1b = self._buf(m, c)
+            self._gemm(W.L[name + ".to_out2"], [ax], [c], 1, 1, m, [(0, 1)], t1b, residual=t1, stream=True)
+            t1 = t1b
         ln2 = self._buf(m, c)
         self._ln(name + ".ln3", t1, m, c, ln2)
         ff = self._buf(m, 4 * c)
@@ -188,7 +229,7 @@ class UNetPlan(PlanBase):
         t2 = self._buf(m, c)
         self._gemm(W.L[name + ".ff2"], [ff], [4 * c], 1, 1, m, [(0, 1)], t2, residual=t1)
         out = self._buf(m, c)
-        self._gemm(W.L[name + ".proj_out"], [t2], [c], 1, 1, m, [(0, 1)], out, residual=x)
+        self._gemm(W.L[name + ".proj_out"], [t2], [c], 1, 1, m, [(0, 1)], out, residual=x, stream=True)
         return out
 
     def _build(self):
@@ -196,7 +237,7 @@ class UNetPlan(PlanBase):
         boc = W.block_out_channels
         h = self.size
         x = self._buf(nb * h * h, boc[0])
-        self._gemm(W.L["conv_in"], [self.x_in], [W.cin_pad], nb, h, h, [(0, 9)], x)
+        self._gemm(W.L["conv_in"], [self.x_in], [W.cin_pad], nb, h, h, [(0, 9)], x, stream=True)
         c = boc[0]
         skips = [(x, c, h)]
         for i, (has_attn, nres, has_down) in enumerate(W.structure):
@@ -207,13 +248,8 @@ class UNetPlan(PlanBase):
                     x = self._transformer(f"down{i}.attn{j}", x, c, h)
                 skips.append((x, c, h))
             if has_down:
-                col = self._buf(nb * (h // 2) * (h // 2), 9 * c)
-                self._op(lambda x=x, h=h, c=c, col=col: nat.im2col_s2(x, nb, h, h, c, 1, col),
-                         tag=f"im2col:{nb * h * h}:down{i}")
+                x = self._down(W.L[f"down{i}.down"], x, c, h, 1)     # Downsample2D: padding 1
                 h //= 2
-                y = self._buf(nb * h * h, c)
-                self._gemm(W.L[f"down{i}.down"], [col], [9 * c], 1, 1, nb * h * h, [(0, 1)], y)
-                x = y
                 skips.append((x, c, h))
         x = self._res("mid.res0", x, c, None, 0, h)
         x = self._transformer("mid.attn0", x, c, h)
@@ -232,11 +268,38 @@ class UNetPlan(PlanBase):
                          tag=f"upsample:{nb * h * h}:up{i}")
                 h *= 2
                 y = self._buf(nb * h * h, c)
-                self._gemm(W.L[f"up{i}.up"], [up], [c], nb, h, h, [(0, 9)], y)
+                self._gemm(W.L[f"up{i}.up"], [up], [c], nb, h, h, [(0, 9)], y, stream=True)
                 x = y
         a = self._buf(nb * h * h, c)
         self._gn("norm_out", x, c, None, 0, h * h, True, a)
         self._gemm(W.L["conv_out"], [a], [c], nb, h, h, [(0, 9)], self.eps)
+        self.link_weight_prefetch()
+
+
+    def set_encoder_hidden_states(self, enc: torch.Tensor) -> None:
+        """enc f32/bf16 [nb, T, D] on the device -> the K / V tensors of every cross-attention layer."""
+        W = self.W
+        if not W.cross_layers:
+            raise RuntimeError("encoder_hidden_states given, but this UNet has no cross-attention layers")
+        nb, T = self.nb, self.ntok_enc
+        if W.object_queries is not None:            # unet.py:335-336: learned queries replace the input
+            enc = W.object_queries.unsqueeze(0).expand(nb, -1, -1)
+        enc = enc.to(device=self.device, dtype=torch.float32).contiguous()
+        if W.hid_proj is not None:                   # unet.py:332-333
+            w, b = W.hid_proj
+            rows = enc.shape[0] * enc.shape[1]
+            proj = torch.empty(rows, w.shape[0], device=self.device)
+            nat.small_linear(enc.reshape(rows, -1), rows, enc.shape[-1], w, b, w.shape[0], False, False, proj, w.shape[0])
+            enc = proj.reshape(enc.shape[0], enc.shape[1], -1)
+        if tuple(enc.shape) != (nb, T, W.cross_dim):
+            raise RuntimeError(f"encoder_hidden_states must be [{nb}, {T}, {W.cross_dim}], got {tuple(enc.shape)}")
+        self.enc_in.copy_(enc.reshape(nb * T, W.cross_dim))
+        old = nat.set_pdl(self.pdl)
+        try:
+            for op in self.kv_ops:
+                op()
+        finally:
+            nat.set_pdl(old)
 
 
 class UNetEngine:
@@ -248,17 +311,33 @@ class UNetEngine:
         with torch.cuda.device(dev):
             self.weights = UNetWeights(unet, dev)
         self.device = dev
-        self.plans: Dict[Tuple[int, int], UNetPlan] = {}
+        self.plans: Dict[Tuple[int, int, int], UNetPlan] = {}
+        self.graphs: Dict[int, "torch.cuda.CUDAGraph"] = {}
+        self.use_graph = bool(getattr(unet, "_use_graph", True))
 
-    def plan(self, nb: int, size: int) -> UNetPlan:
-        key = (nb, size)
+    def plan(self, nb: int, size: int, ntok_enc: int = 0) -> UNetPlan:
+        key = (nb, size, ntok_enc)
         if key not in self.plans:
             with torch.cuda.device(self.device):
-                self.plans[key] = UNetPlan(self.weights, nb, size)
+                self.plans[key] = UNetPlan(self.weights, nb, size, ntok_enc)
         return self.plans[key]
 
+    def _graph_for(self, plan: UNetPlan):
+        """The drop-in `unet(...)` call replays ONE captured graph of the plan's launch list instead of issuing its
+        ~264 launches through ctypes (each igemm launch also re-encodes up to four tensor maps on the host)."""
+        g = self.graphs.get(id(plan))
+        if g is None:
+            plan.run()                       # warm-up outside capture (lazy kernel attribute setup)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                plan.run()
+            self.graphs[id(plan)] = g
+        return g
+
     @torch.no_grad()
-    def forward(self, sample: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+    def forward(self, sample: torch.Tensor, timesteps: torch.Tensor,
+                encoder_hidden_states: torch.Tensor = None) -> torch.Tensor:
         """sample f32 NCHW [B, C, L, L] (C = conv_in channels), timesteps [B] -> eps f32 NCHW [B, 4, L, L]."""
         nb, c, hgt, wid = sample.shape
         if hgt != wid:
@@ -266,13 +345,27 @@ class UNetEngine:
                                "trainers_ldm_cond.py:1089)")
         if c != self.weights.in_channels:
             raise RuntimeError(f"UNet expects {self.weights.in_channels} input channels, got {c}")
-        plan = self.plan(nb, hgt)
+        W = self.weights
+        ntok_enc = 0
+        if W.cross_layers:
+            if W.object_queries is not None:
+                ntok_enc = W.object_queries.shape[0]
+            elif encoder_hidden_states is None:
+                raise RuntimeError("this UNet kept its cross-attention: encoder_hidden_states is required")
+            else:
+                ntok_enc = encoder_hidden_states.shape[1]
+        plan = self.plan(nb, hgt, ntok_enc)
         with torch.cuda.device(self.device):
             tf = timesteps.to(device=self.device, dtype=torch.float32).contiguous()
             self.weights.time_embedding(tf, plan.temb)
             nat.nchw_to_nhwc_bf16(sample.contiguous(), nb, c, hgt * wid, self.weights.cin_pad, 0, 1.0, 0.0,
                                   plan.x_in)
-            plan.run()
+            if W.cross_layers:
+                plan.set_encoder_hidden_states(encoder_hidden_states)
+            if self.use_graph and not torch.cuda.is_current_stream_capturing():
+                self._graph_for(plan).replay()
+            else:
+                plan.run()
             out = torch.empty(nb, 4, hgt, wid, device=self.device, dtype=torch.float32)
             nat.nhwc_f32_to_nchw(plan.eps, nb, 4, hgt * wid, 4, 1.0, out)
         return out

@@ -48,8 +48,7 @@ class ImageEncoderWeights(WeightsBase):
                 chans.append((r.in_channels, r.out_channels))
             has_down = blk.downsamplers is not None
             if has_down:
-                d = blk.downsamplers[0].conv
-                self._gemm(f"down{i}.down", pk.pack_conv3x3_im2col(d.weight), d.bias, d.out_channels)
+                self._conv_s2(f"down{i}.down", blk.downsamplers[0].conv)
             self.blocks.append((chans, has_down))
         mid = enc.mid_block
         for j, r in enumerate(mid.resnets):
@@ -73,8 +72,8 @@ class ImageEncoderWeights(WeightsBase):
 class ImageEncoderPlan(PlanBase):
     """x_in bf16 [nb*S*S, 16] (RGB in channels 0..2, already scaled to [-1,1]) -> moments f32 [nb*(S/8)^2, 8]."""
 
-    def __init__(self, W: ImageEncoderWeights, nb: int, size: int):
-        super().__init__(W, nb)
+    def __init__(self, W: ImageEncoderWeights, nb: int, size: int, allow_split: bool = True):
+        super().__init__(W, nb, allow_split)
         self.size = size
         self.x_in = torch.zeros(nb * size * size, W.cin_pad, device=self.device, dtype=torch.bfloat16)
         self._build()
@@ -89,17 +88,26 @@ class ImageEncoderPlan(PlanBase):
         self._gemm(W.L["mid.attn.q"], [g], [c], 1, 1, m, [(0, 1)], q)
         self._gemm(W.L["mid.attn.k"], [g], [c], 1, 1, m, [(0, 1)], k)
         vt = self._buf(c, hw)
-        s = self._buf(hw, hw, torch.float32)
-        p = self._buf(hw, hw)
+        # scores are produced in query chunks so that the f32 S / bf16 P scratch stays bounded (2048 x hw: 128 MB +
+        # 64 MB at a 1024x1024 image instead of 1 GB + 512 MB) and is shared by all images of the batch
+        qc = min(hw, max(128, (32 * 1024 * 1024) // hw // 128 * 128))
+        s = self._buf(qc, hw, torch.float32)
+        p = self._buf(qc, hw)
         o = self._buf(m, c)
         scale = 1.0 / math.sqrt(c)
         for b in range(nb):
             gb, qb, kb, ob = (t[b * hw:(b + 1) * hw] for t in (g, q, k, o))
-            # V^T [c, hw] = W_v [c, c] . g_b^T : "activations" = W_v rows, "weights" = g_b rows
+            # V^T [c, hw] = W_v [c, c] . g_b^T : "activations" = W_v rows, "weights" = g_b rows.  The B operands of
+            # these three products (g_b, k_b, V^T) are written by earlier launches of this stream: they are NOT
+            # static weights, so the kernel must not fetch them before its grid-dependency wait (_Layer without
+            # `static` -> weight_static = 0)
             self._gemm(_Layer(gb, None, hw), [W.wv], [c], 1, 1, c, [(0, 1)], vt, allow_split=False)
-            self._gemm(_Layer(kb, None, hw), [qb], [c], 1, 1, hw, [(0, 1)], s, allow_split=False)
-            self._op(lambda s=s, p=p: nat.softmax_rows(s, hw, hw, scale, p))
-            self._gemm(_Layer(vt, W.bv, c), [p], [hw], 1, 1, hw, [(0, 1)], ob, allow_split=False)
+            for r0 in range(0, hw, qc):
+                rows = min(qc, hw - r0)
+                sc, pc = s[:rows], p[:rows]
+                self._gemm(_Layer(kb, None, hw), [qb[r0:r0 + rows]], [c], 1, 1, rows, [(0, 1)], sc, allow_split=False)
+                self._op(lambda sc=sc, pc=pc, rows=rows: nat.softmax_rows(sc, rows, hw, scale, pc))
+                self._gemm(_Layer(vt, W.bv, c), [pc], [hw], 1, 1, rows, [(0, 1)], ob[r0:r0 + rows], allow_split=False)
         out = self._buf(m, c)
         self._gemm(W.L["mid.attn.proj"], [o], [c], 1, 1, m, [(0, 1)], out, residual=x)
         return out
@@ -115,12 +123,8 @@ class ImageEncoderPlan(PlanBase):
                 x = self._resnet(f"down{i}.res{j}", x, ci, None, 0, h)
                 c = co
             if has_down:
-                col = self._buf(nb * (h // 2) * (h // 2), 9 * c)
-                self._op(lambda x=x, h=h, c=c, col=col: nat.im2col_s2(x, nb, h, h, c, 0, col))
+                x = self._down(W.L[f"down{i}.down"], x, c, h, 0)     # F.pad(0,1,0,1) + stride-2 conv, padding 0
                 h //= 2
-                y = self._buf(nb * h * h, c)
-                self._gemm(W.L[f"down{i}.down"], [col], [9 * c], 1, 1, nb * h * h, [(0, 1)], y)
-                x = y
         x = self._resnet("mid.res0", x, c, None, 0, h)
         x = self._attention(x, c, h)
         x = self._resnet("mid.res1", x, c, None, 0, h)
@@ -176,7 +180,7 @@ class SegVAEWeights(WeightsBase):
                     if stride == 1:
                         self._gemm(name, pk.pack_conv3x3(_pad_cin(m, cpad)), m.bias, m.out_channels)
                     else:
-                        self._gemm(name, pk.pack_conv3x3_im2col(m.weight), m.bias, m.out_channels)
+                        self._conv_s2(name, m)
                     spec.append(("conv", name, cin, cpad, m.out_channels, stride, silu))
                 elif isinstance(m, nn.GroupNorm):
                     self._norm(f"enc.{idx}", m)
@@ -235,11 +239,8 @@ class SegEncoderPlan(PlanBase):
                     y = self._buf(nb * h * h, cout, torch.float32 if final else torch.bfloat16)
                     self._gemm(W.L[name], [x], [c], nb, h, h, [(0, 9)], y, act=act)
                 else:
-                    col = self._buf(nb * (h // 2) * (h // 2), 9 * c)
-                    self._op(lambda x=x, h=h, c=c, col=col: nat.im2col_s2(x, nb, h, h, c, 1, col))
+                    y = self._down(W.L[name], x, c, h, 1, act=act)        # nn.Conv2d(stride=2, padding=1)
                     h //= 2
-                    y = self._buf(nb * h * h, cout)
-                    self._gemm(W.L[name], [col], [9 * c], 1, 1, nb * h * h, [(0, 1)], y, act=act)
                 x, c = y, cout
             else:
                 _, name, cn, silu = s
@@ -260,22 +261,24 @@ class ImageEncoderEngine:
         self.device = dev
         with torch.cuda.device(dev):
             self.weights = ImageEncoderWeights(vae, dev)
-        self.plans: Dict[Tuple[int, int], ImageEncoderPlan] = {}
+        self.plans: Dict[Tuple[int, int, bool], ImageEncoderPlan] = {}
 
-    def plan(self, nb, size):
-        if (nb, size) not in self.plans:
+    def plan(self, nb, size, no_split: bool = False):
+        key = (nb, size, no_split)
+        if key not in self.plans:
             with torch.cuda.device(self.device):
-                self.plans[(nb, size)] = ImageEncoderPlan(self.weights, nb, size)
-        return self.plans[(nb, size)]
+                self.plans[key] = ImageEncoderPlan(self.weights, nb, size, allow_split=not no_split)
+        return self.plans[key]
 
     @torch.no_grad()
-    def encode(self, x: torch.Tensor, in_scale: float = 1.0, in_shift: float = 0.0) -> torch.Tensor:
+    def encode(self, x: torch.Tensor, in_scale: float = 1.0, in_shift: float = 0.0,
+               no_split: bool = False) -> torch.Tensor:
         """x f32 NCHW [B,3,S,S] -> moments f32 NCHW [B,8,S/8,S/8]; (in_scale, in_shift) fuses the
         caller's `2*x-1` (trainers_ldm_cond.py:369) into the layout conversion."""
         nb, c, h, w = x.shape
         if h != w or c != self.weights.in_channels:
             raise RuntimeError(f"GeneralVAEImage.encode expects [B,{self.weights.in_channels},S,S], got {tuple(x.shape)}")
-        plan = self.plan(nb, h)
+        plan = self.plan(nb, h, no_split)
         with torch.cuda.device(self.device):
             nat.nchw_to_nhwc_bf16(x.float().contiguous(), nb, c, h * w, self.weights.cin_pad, 0, in_scale,
                                   in_shift, plan.x_in)
@@ -339,6 +342,40 @@ class SegVAEEngine:
             prob = torch.empty(nb, 2 * s, 2 * s, device=self.device, dtype=torch.float32)
             nat.bilinear2x_argmax(plan.logits, nb, s, s, k, k, ids, prob)
         return ids, prob
+
+    @torch.no_grad()
+    def decode_panoptic(self, z: torch.Tensor, sizes, crops=None, scale: float = 1.0, mask_th: float = 0.5,
+                        count_th: int = 512, overlap_th: float = 0.5, ignore_label: int = 0,
+                        threshold_output: bool = True):
+        """Decode + the whole per-image post-processing of `compute_pq`
+        (/root/reference/ldmseg/trainers/trainers_ldm_cond.py:1243-1313) on the device.
+
+        z [B,4,L,L]; sizes = [(h, w)] original image sizes; crops = [(y0, x0, ch, cw)] padding crops on the 8L x 8L
+        grid (default: the whole grid).  Returns (ids u8 [B, max_hw] on the device -- image i is
+        ids[i, :h*w].view(h, w), 0 = void, id = class + 1 -- and keep int32 [B, 128]: keep[i, c] = 1 iff segment
+        id c + 1 of image i survives = the reference's `segments_info`)."""
+        with torch.cuda.device(self.device):
+            plan = self._run_decoder(z, scale)
+            nb, s, k = plan.nb, plan.out_size, self.weights.num_classes
+            if len(sizes) != nb:
+                raise RuntimeError("decode_panoptic: one (h, w) per image")
+            geom = []
+            for i, (h, w) in enumerate(sizes):
+                y0, x0, ch, cw = crops[i] if crops is not None else (0, 0, 2 * s, 2 * s)
+                geom.append([int(h), int(w), int(y0), int(x0), int(ch), int(cw)])
+            max_hw = max(g[0] * g[1] for g in geom)
+            stride = (max_hw + 15) // 16 * 16
+            gd = torch.tensor(geom, dtype=torch.int32).to(self.device, non_blocking=True)
+            pred = torch.empty(nb, stride, device=self.device, dtype=torch.int16)
+            area = torch.empty(nb, 128, device=self.device, dtype=torch.int32)
+            orig = torch.empty(nb, 128, device=self.device, dtype=torch.int32)
+            ids = torch.empty(nb, stride, device=self.device, dtype=torch.uint8)
+            keep = torch.empty(nb, 128, device=self.device, dtype=torch.int32)
+            nat.panoptic_resample(plan.logits, nb, s, k, k, gd, max_hw, stride, mask_th, threshold_output, pred,
+                                  area, orig)
+            nat.panoptic_filter(pred, nb, gd, max_hw, stride, area, orig, count_th, overlap_th, ignore_label, ids,
+                                keep)
+        return ids, keep
 
     @torch.no_grad()
     def encode(self, x: torch.Tensor) -> torch.Tensor:

@@ -144,6 +144,7 @@ class UNet(nn.Module):
     def define_learnable_embedding(self, in_channels, out_channels):
         assert self.encoder_hid_proj is None
         self.object_queries = nn.Embedding(in_channels, out_channels)
+        self._engine = None
 
     def define_separate_encoder(self, add_adaptor: bool = False, init_mode_adaptor: str = "random"):
         raise NotImplementedError("the dual-encoder variant is off by default and not built (SURVEY.md §2 row 1)")
@@ -172,6 +173,7 @@ class UNet(nn.Module):
 
     def modify_encoder_hidden_state_proj(self, in_channels: int, out_channels: int) -> None:
         self.encoder_hid_proj = nn.Linear(in_channels, out_channels)
+        self._engine = None
 
     def modify_encoder(self, in_channels: int = 4, init_mode_seg: str = "copy", init_mode_image: str = "copy",
                        cond_channels: int = 0, init_mode_cond: str = "zero", separate_conv: bool = False,
@@ -250,12 +252,10 @@ class UNet(nn.Module):
                                "fallback (the CPU oracle lives under oracle/ and is test infrastructure)")
         if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
             raise NotImplementedError("additional residuals (dual encoder / ControlNet) are not built")
-        if hasattr(self, "object_queries") or self.encoder_hid_proj is not None:
-            raise NotImplementedError("conditioned variants (cross-attention) are not built (SURVEY.md §8f row 3)")
         if not torch.is_tensor(timestep):
             timestep = torch.tensor(timestep, device=sample.device)
         timesteps = timestep.to(sample.device).expand(sample.shape[0])  # accepts either device (Q5)
-        out = self._get_engine().forward(sample.float(), timesteps)
+        out = self._get_engine().forward(sample.float(), timesteps, encoder_hidden_states)
         out = out.to(sample.dtype) if sample.dtype != torch.float32 else out
         if not return_dict:
             return (out,)

@@ -292,6 +292,23 @@ class GeneralVAESeg(nn.Module):
         without materialising the logits (what trainers_ldm_cond.py:428-433 computes from them)."""
         return self._get_engine().decode_ids(z)
 
+    @torch.no_grad()
+    def decode_panoptic(self, z, sizes, crops=None, mask_th: float = 0.5, count_th: int = 512,
+                        overlap_th: float = 0.5, ignore_label: int = 0, threshold_output: bool = True):
+        """Extension: decode + the per-image post-processing of `TrainerDiffusion.compute_pq`
+        (trainers_ldm_cond.py:1243-1313: resize to the original size, argmax, mask_th, count_th / overlap_th
+        segment filtering) on the device.  Returns [(panoptic_seg uint8 [h, w] CPU tensor, segment ids)] -- the
+        reference's `processed_results[i]["panoptic_seg"]` with `segments_info` reduced to its ids."""
+        if not z.is_cuda:
+            raise RuntimeError("ldmseg_b200.GeneralVAESeg.decode_panoptic needs CUDA tensors (no CPU fallback)")
+        ids, keep = self._get_engine().decode_panoptic(z, sizes, crops, 1.0, mask_th, count_th, overlap_th,
+                                                       ignore_label, threshold_output)
+        ids, keep = ids.cpu(), keep.cpu()            # uint8 ids + a 128-entry table per image: the only D2H traffic
+        out = []
+        for i, (h, w) in enumerate(sizes):
+            out.append((ids[i, : h * w].view(h, w), [int(c) + 1 for c in keep[i].nonzero().flatten()]))
+        return out
+
     def forward(self, sample, sample_posterior: bool = True, return_dict: bool = True, generator=None,
                 rgb_sample=None, valid_mask=None):
         x = sample

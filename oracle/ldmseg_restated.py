@@ -288,26 +288,34 @@ def encode_inputs(images, vae_image, scaling_factor=0.18215):
 
 @torch.no_grad()
 def sample(unet, scheduler, rgb_latents, num_inference_steps=50, seed=42, self_condition=True,
-           noise=None, return_all=False, mask=None, known_latents=None, ddpm=False):
-    """ldmseg/trainers/trainers_ldm_cond.py:1045-1170 (no descriptors, multiplier = 1).
+           noise=None, return_all=False, mask=None, known_latents=None, ddpm=False,
+           encoder_hidden_states=None, guidance_scale=7.5):
+    """ldmseg/trainers/trainers_ldm_cond.py:1045-1170.  `encoder_hidden_states` [2B, T, D] (uncond | cond rows,
+    as built at :1104 / :1116) switches on the doubled batch + guidance combine of :1098-1123, 1143-1146.
     Extensions (labelled, absent in the reference): `mask`/`known_latents` inpainting blend,
-    `ddpm` ancestral noise."""
+    `ddpm` ancestral noise (generator seeded seed + 1)."""
     scheduler.set_timesteps_inference(num_inference_steps)               # :1078-1080
     b, _, L, _ = rgb_latents.shape
     gen = torch.Generator().manual_seed(seed) if seed is not None else None  # :1088
     latents = noise if noise is not None else torch.randn((b, 4, L, L), generator=gen)  # :1090
+    multiplier = 2 if encoder_hidden_states is not None else 1          # :1098-1119
     latents = latents * scheduler.init_noise_sigma                       # :1121
+    rgb_latents = torch.cat([rgb_latents] * multiplier)                  # :1123
     condition = torch.zeros_like(rgb_latents)                            # :1126
     fixed_noise = latents.clone()
-    extra = torch.Generator().manual_seed(1234)
+    extra = torch.Generator().manual_seed((seed if seed is not None else 0) + 1)
     alls = []
     ts = scheduler.timesteps
     for i, t in enumerate(ts):                                           # :1127
+        lmi = torch.cat([latents] * multiplier)                          # :1128
         if self_condition:
-            inp = torch.cat([latents, rgb_latents, condition], dim=1)    # :1133
+            inp = torch.cat([lmi, rgb_latents, condition], dim=1)        # :1133
         else:
-            inp = torch.cat([latents, rgb_latents], dim=1)               # :1135
-        eps = unet(inp.float(), t, encoder_hidden_states=None).sample    # :1141
+            inp = torch.cat([lmi, rgb_latents], dim=1)                   # :1135
+        eps = unet(inp.float(), t, encoder_hidden_states=encoder_hidden_states).sample    # :1141
+        if multiplier > 1:                                               # :1143-1146
+            eu, et = eps.chunk(2)
+            eps = eu + guidance_scale * (et - eu)
         if ddpm and i != len(ts) - 1:
             z = torch.randn(latents.shape, generator=extra)
             out = scheduler.step_ddpm(eps, t, latents, z)
@@ -335,3 +343,70 @@ def decode_latents(latents, vae_semseg, return_logits=True):
     if return_logits:
         return logits
     return torch.argmax(logits, dim=1)                                   # :428
+
+
+# --------------------------------------------------------------------------------------------
+def panoptic_postprocess(masks_logits, sizes, mask_th=0.5, count_th=512, overlap_th=0.5, ignore_label=0,
+                         threshold_output=True, padding_masks=None):
+    """ldmseg/trainers/trainers_ldm_cond.py:1261-1313, per image: (crop_padding :1264) -> bilinear resize of the
+    logits to the original (h, w) (:1267-1272) -> argmax (:1275) -> softmax-max < mask_th -> -1 (:1276-1284) ->
+    per-segment filtering by area `count_th` and by the overlap of the argmax region with the thresholded sigmoid
+    mask (:1293-1313).  masks_logits f32 [B, C, H, W] (already at the RGB size, :1252-1257), sizes [(h, w)].
+    Returns [(panoptic_seg int64 [h, w] with 0 = void, [segment ids])] -- `panoptic_pred + 1`, `segments_info` ids."""
+    out = []
+    for i, logit in enumerate(masks_logits):
+        if padding_masks is not None:                                    # crop_padding, :1172-1178
+            co = padding_masks[i].nonzero()
+            y0, y1, x0, x1 = co[:, 0].min(), co[:, 0].max(), co[:, 1].min(), co[:, 1].max()
+            logit = logit[:, y0:y1 + 1, x0:x1 + 1]
+        h, w = sizes[i]
+        r = F.interpolate(logit[None].float(), size=(h, w), mode="bilinear", align_corners=False)[0]   # :1267-1272
+        pred = torch.argmax(r, dim=0)                                    # :1275
+        if threshold_output:
+            probs = F.softmax(r, dim=0).max(dim=0)[0]                    # :1277,1283
+            pred[probs < mask_th] = -1                                   # :1284
+        pred = pred.numpy()
+        sig = torch.sigmoid(r).numpy()                                   # :1288-1289
+        ids = []
+        for label, count in zip(*np.unique(pred, return_counts=True)):   # :1293
+            if count < count_th or label in {-1, ignore_label}:          # :1296-1298
+                pred[pred == label] = -1
+                continue
+            original = sig[label] >= mask_th                             # :1301
+            if (pred == label).sum() / original.sum() < overlap_th:      # :1302-1304
+                pred[pred == label] = -1
+                continue
+            ids.append(int(label) + 1)                                   # :1306-1312
+        out.append((pred + 1, ids))                                      # :1313
+    return out
+
+
+def panoptic_filter(pred, area, orig_area, mask_th_unused=None, count_th=512, overlap_th=0.5, ignore_label=0):
+    """The integer half of the routine above on its own (bit-exact target of the CUDA filter kernel): `pred` int
+    [h, w] with -1 = below threshold, `area[l]` = #pixels with pred == l, `orig_area[l]` = #pixels whose sigmoid
+    for class l reaches mask_th.  Returns (pred + 1 with dropped segments zeroed, kept ids)."""
+    pred = pred.copy()
+    ids = []
+    for label in range(len(area)):
+        count = int(area[label])
+        if count == 0:
+            continue
+        if count < count_th or label == ignore_label:
+            pred[pred == label] = -1
+            continue
+        if count / float(orig_area[label]) < overlap_th:
+            pred[pred == label] = -1
+            continue
+        ids.append(label + 1)
+    return pred + 1, ids
+
+
+@torch.no_grad()
+def self_condition_estimate(unet, scheduler, latents, rgb_latents, noise, timesteps, encoder_hidden_states=None):
+    """The training step's no-grad forward (ldmseg/trainers/trainers_ldm_cond.py:813-831): add_noise at per-sample
+    timesteps, UNet on cat[noisy, rgb, zeros], remove_noise -> the self-conditioning estimate of x0."""
+    noisy = scheduler.add_noise(latents, noise, timesteps)               # :820
+    cond = torch.zeros_like(noisy)                                       # :826
+    inp = torch.cat([noisy, rgb_latents, cond], dim=1)                   # :828
+    pred = unet(inp, timesteps, encoder_hidden_states=encoder_hidden_states).sample   # :830
+    return noisy, pred, scheduler.remove_noise(noisy, pred, timesteps)   # :831

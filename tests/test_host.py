@@ -20,7 +20,8 @@ def test_library_exports_every_declared_symbol(_built_library):
         assert hasattr(lib, name), f"{name} declared in include/ldmseg_b200.h but not exported"
     from ldmseg import _native as nat
     assert set(nat.EXPORTS) == declared
-    assert nat.load().ldmseg_version() == 1
+    abi = int(re.search(r"#define LDMSEG_ABI_VERSION (\d+)", hdr).group(1))
+    assert abi >= 2 and nat.load().ldmseg_version() == abi
 
 
 def test_igemm_params_struct_layout_matches_header():
@@ -29,9 +30,9 @@ def test_igemm_params_struct_layout_matches_header():
     hdr = open(os.path.join(ROOT, "include", "ldmseg_b200.h")).read()
     body = hdr[hdr.index("typedef struct ldmseg_igemm_params {"):hdr.index("} ldmseg_igemm_params;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = re.findall(r"([a-z_]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
+    names = re.findall(r"([a-z_0-9]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
     fields = [f[0] for f in nat.IgemmParams._fields_]
-    assert fields == names and len(fields) == 31
+    assert fields == names and len(fields) == 39
 
 
 def test_product_scheduler_host_logic_matches_reference(golden_dir):
