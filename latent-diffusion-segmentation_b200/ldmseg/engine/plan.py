@@ -304,11 +304,11 @@ class PlanBase:
             if f0 is not None and (src1 is None or f1 is not None):
                 src0, src1 = f0, f1
             self._op(lambda: nat.groupnorm_apply_cs(src0, c0, cs0, src1, c1, cs1, nb, hw, groups, g, b, eps, silu,
-                                                    out), tag=f"gn:{nb * hw}:{name}")
+                                                    out), tag=f"gn:{nb * hw}:{name}:c{c0 + c1}")
             return
         stats = self.gn_stats
         self._op(lambda: nat.groupnorm(src0, c0, src1, c1, nb, hw, groups, g, b, eps, silu, out, stats), 3,
-                 tag=f"gn3:{nb * hw}:{name}")
+                 tag=f"gn3:{nb * hw}:{name}:c{c0 + c1}")
 
     def _ln(self, name, src, rows, c, out, silu=False):
         g, b, eps = self.W.norms[name]

@@ -369,3 +369,46 @@ class UNetEngine:
             out = torch.empty(nb, 4, hgt, wid, device=self.device, dtype=torch.float32)
             nat.nhwc_f32_to_nchw(plan.eps, nb, 4, hgt * wid, 4, 1.0, out)
         return out
+
+    @torch.no_grad()
+    def self_condition_forward(self, scheduler, latents: torch.Tensor, rgb_latents: torch.Tensor,
+                               noise: torch.Tensor, timesteps: torch.Tensor,
+                               encoder_hidden_states: torch.Tensor = None):
+        """The training step's no-grad forward on the sampling kernels
+        (/root/reference/ldmseg/trainers/trainers_ldm_cond.py:813-831): per-sample timesteps,
+
+            noisy = add_noise(latents, noise, t);  pred = unet(cat[noisy, rgb, 0], t);  cond = remove_noise(noisy, pred, t)
+
+        `add_noise` writes the fp32 noisy latents AND channels 0..3 of the bf16 channel-last UNet input in one
+        kernel (no torch.cat, no cast); the forward replays the captured graph of the plan.
+        Returns (noisy_latents, pred, condition) f32 NCHW."""
+        nb, c4, hgt, wid = latents.shape
+        W = self.weights
+        if hgt != wid or c4 != 4 or W.in_channels not in (8, 12):
+            raise RuntimeError("self_condition_forward: [B,4,L,L] latents and an 8- or 12-channel conv_in")
+        hw = hgt * wid
+        ntok_enc = 0
+        if W.cross_layers:
+            ntok_enc = W.object_queries.shape[0] if W.object_queries is not None else encoder_hidden_states.shape[1]
+        plan = self.plan(nb, hgt, ntok_enc)
+        with torch.cuda.device(self.device):
+            t = timesteps.to(device=self.device, dtype=torch.int64).reshape(-1).contiguous()
+            lat = latents.float().contiguous()
+            nz = noise.float().contiguous()
+            noisy = torch.empty_like(lat)
+            plan.x_in.zero_()                                           # condition = zeros (:826)
+            nat.noise_mix(lat, nz, t, scheduler._acp_on(self.device), nb, 4 * hw, 1.0, 0, noisy, plan.x_in, hw,
+                          W.cin_pad)
+            nat.nchw_to_nhwc_bf16(rgb_latents.float().contiguous(), nb, 4, hw, W.cin_pad, 4, 1.0, 0.0, plan.x_in)
+            W.time_embedding(t.float(), plan.temb)
+            if W.cross_layers:
+                plan.set_encoder_hidden_states(encoder_hidden_states)
+            if self.use_graph and not torch.cuda.is_current_stream_capturing():
+                self._graph_for(plan).replay()
+            else:
+                plan.run()
+            pred = torch.empty(nb, 4, hgt, wid, device=self.device, dtype=torch.float32)
+            nat.nhwc_f32_to_nchw(plan.eps, nb, 4, hw, 4, 1.0, pred)
+            cond = torch.empty_like(pred)
+            nat.noise_mix(noisy, pred, t, scheduler._acp_on(self.device), nb, 4 * hw, 1.0, 1, cond)
+        return noisy, pred, cond

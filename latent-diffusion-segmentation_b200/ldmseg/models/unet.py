@@ -232,6 +232,17 @@ class UNet(nn.Module):
             else:
                 raise NotImplementedError(f"layer {layer} not implemented")
 
+    @torch.no_grad()
+    def self_condition_estimate(self, scheduler, latents, rgb_latents, noise, timesteps,
+                                encoder_hidden_states=None):
+        """Extension: the no-grad forward of the training step (trainers_ldm_cond.py:813-831) on the sampling
+        kernels -- add_noise at per-sample timesteps, UNet on cat[noisy, rgb, zeros], remove_noise.
+        Returns (noisy_latents, pred, condition)."""
+        if not latents.is_cuda:
+            raise RuntimeError("ldmseg_b200.UNet.self_condition_estimate needs CUDA tensors (no CPU fallback)")
+        return self._get_engine().self_condition_forward(scheduler, latents, rgb_latents, noise, timesteps,
+                                                         encoder_hidden_states)
+
     # ------------------------------------------------------------------ forward
     def _get_engine(self):
         if self._engine is None:

@@ -129,15 +129,40 @@ class DDIMNoiseScheduler(object):
         view = (-1,) + (1,) * (like.dim() - 1)
         return (a ** 0.5).view(view), ((1 - a) ** 0.5).view(view)
 
+    def _acp_on(self, dev):
+        acp = self._acp_dev.get(dev)
+        if acp is None:
+            acp = self.alphas_cumprod.to(device=dev, dtype=torch.float32).contiguous()
+            self._acp_dev[dev] = acp
+        return acp
+
+    def _mix_cuda(self, x, noise, timesteps, scale, mode):
+        """CUDA tensors: one fused kernel, per-sample timesteps gathered on the device (ldmseg_noise_mix)."""
+        xs, nz = x.contiguous().float(), noise.contiguous().float()
+        nb = xs.shape[0]
+        t = timesteps.to(device=xs.device, dtype=torch.int64).reshape(-1)
+        if t.numel() == 1 and nb > 1:
+            t = t.expand(nb)
+        t = t.contiguous()
+        if t.numel() != nb:
+            raise RuntimeError("add_noise / remove_noise: one timestep per sample")
+        out = torch.empty_like(xs)
+        nat.noise_mix(xs, nz, t, self._acp_on(xs.device), nb, xs[0].numel(), float(scale), mode, out)
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
     def add_noise(self, original_samples, noise, timesteps, scale: float = 1.0,
                   mask_noise_perc: Optional[float] = None):
-        sa, sb = self._gather(timesteps, original_samples)
         if mask_noise_perc is not None:
             noise *= torch.rand_like(original_samples) < mask_noise_perc
+        if original_samples.is_cuda:
+            return self._mix_cuda(original_samples, noise, timesteps, scale, 0)
+        sa, sb = self._gather(timesteps, original_samples)
         return sa * scale * original_samples + sb * noise
 
     @torch.no_grad()
     def remove_noise(self, noisy_samples, noise, timesteps, scale: float = 1.0):
+        if noisy_samples.is_cuda:
+            return self._mix_cuda(noisy_samples, noise, timesteps, scale, 1)
         sa, sb = self._gather(timesteps, noisy_samples)
         return (noisy_samples - sb * noise) / (sa * scale)
 
@@ -158,11 +183,7 @@ class DDIMNoiseScheduler(object):
         ratio = self.num_train_timesteps // self.num_inference_steps
         ptype = _PTYPE[self.prediction_type]
         if torch.is_tensor(timestep) and timestep.is_cuda:
-            dev = xs.device
-            acp = self._acp_dev.get(dev)
-            if acp is None:
-                acp = self.alphas_cumprod.to(device=dev, dtype=torch.float32).contiguous()
-                self._acp_dev[dev] = acp
+            acp = self._acp_on(xs.device)
             t = timestep.reshape(-1)[:1].to(torch.int64)
             nat.ddim_step_indexed(mo, xs, t, acp, ratio, float(self.final_alpha_cumprod), ptype,
                                   self.clip_sample, float(self.clip_sample_range),

@@ -13,8 +13,8 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_pair", "gn_fused", "norm", "attn_simple",
-          "attn", "elementwise"]
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_pair", "igemm_s2", "igemm_f32stream",
+          "gn_fused", "norm", "attn_simple", "attn", "xattn", "elementwise", "sampler", "panoptic", "vae_pdl"]
 
 
 def report(name, got, ref, tol):
@@ -37,6 +37,9 @@ def run_group(group):
     from ldmseg import _pack as pk
 
     torch.manual_seed(0)
+    # the references below must be fp32, not TF32 (cudnn.allow_tf32 defaults to True)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     dev = "cuda"
     ok = True
     bf = torch.bfloat16
@@ -364,6 +367,259 @@ def run_group(group):
         print(f"{'PASS' if agree > 0.999 else 'FAIL'} bilinear2x_argmax agreement={agree:.5f}")
         ok &= agree > 0.999
         ok &= report("bilinear2x_argmax maxprob", mp, ref.softmax(1).max(1)[0], 1e-4)
+
+    elif group == "igemm_s2":
+        # 3x3 stride-2 convolutions through the TMA traversal stride (no im2col): UNet Downsample2D (padding 1)
+        # and the AutoencoderKL encoder (F.pad(0,1,0,1), padding 0); (nb, hout) output geometry
+        for (nb, hout, cin, cout, pad, kw) in [
+                (1, 32, 320, 320, 1, {}), (2, 16, 640, 640, 1, {}), (1, 8, 1280, 1280, 1, dict(split_k=4)),
+                (1, 4, 1280, 1280, 1, {}), (1, 256, 128, 128, 0, {}), (1, 128, 256, 256, 0, {}),
+                (2, 64, 512, 512, 0, {}), (1, 256, 32, 64, 1, dict(act=nat.ACT_SILU)), (1, 32, 320, 320, 1, dict(pair=True, block_n=160)),
+                (3, 8, 64, 64, 0, dict(simple=True))]:
+            hin = 2 * hout
+            x = rnd(nb * hin * hin, cin)
+            wt = torch.randn(cout, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
+            b = torch.randn(cout, device=dev)
+            tiled = True
+            wb = pk.to_bf16(pk.tile_pack(pk.pack_conv3x3(wt)))
+            out = torch.full((nb * hout * hout, cout), float("nan"), device=dev, dtype=bf)
+            split = kw.get("split_k", 0)
+            ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev) if split > 1 else None
+            cnt = torch.zeros(8192, device=dev, dtype=torch.int32) if split > 1 else None
+            p = nat.make_igemm_params([x], [cin], nb, hout, hout, [(0, 9)], wb, cout, out, cout, bias=b,
+                                      act=kw.get("act", nat.ACT_NONE), block_n=kw.get("block_n", 0), split_k=split,
+                                      workspace=ws, counters=cnt, weight_tiled=tiled, pair=kw.get("pair", False),
+                                      weight_static=True, pdl=True, conv_stride=2, conv_pad=pad)
+            nat.igemm(p, simple=kw.get("simple", False))
+            torch.cuda.synchronize()
+            xi = x.float().reshape(nb, hin, hin, cin).permute(0, 3, 1, 2)
+            wq = wt.to(bf).float()
+            if pad == 1:
+                ref = F.conv2d(xi, wq, b, stride=2, padding=1)
+            else:
+                ref = F.conv2d(F.pad(xi, (0, 1, 0, 1)), wq, b, stride=2, padding=0)
+            if kw.get("act") == nat.ACT_SILU:
+                ref = F.silu(ref)
+            ref = ref.permute(0, 2, 3, 1).reshape(nb * hout * hout, cout)
+            ok &= report(f"igemm conv3x3 stride 2 (TMA) {nb}x{hin}->{hout} {cin}->{cout} pad={pad} {kw}", out, ref, 1e-2)
+    elif group == "igemm_f32stream":
+        # fp32 residual stream: f32 residual in, f32 out + bf16 shadow, statistics of the f32 values
+        for (nb, h, cin, cout, taps, kw) in [(2, 32, 320, 320, 9, {}), (1, 64, 320, 320, 1, {}),
+                                             (1, 16, 1280, 1280, 9, dict(split_k=6)), (1, 64, 320, 4, 9, {}),
+                                             (2, 8, 64, 64, 9, dict(simple=True))]:
+            m = nb * h * h
+            x = rnd(m, cin)
+            if taps == 9:
+                wt = torch.randn(cout, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
+                wb = pk.to_bf16(pk.tile_pack(pk.pack_conv3x3(wt)))
+            else:
+                wt = torch.randn(cout, cin, device=dev) / cin ** 0.5
+                wb = pk.to_bf16(pk.tile_pack(pk.pack_linear(wt)))
+            b = torch.randn(cout, device=dev)
+            res = torch.randn(m, cout, device=dev)
+            out = torch.full((m, cout), float("nan"), device=dev)
+            out2 = torch.full((m, cout), float("nan"), device=dev, dtype=bf)
+            st = torch.zeros(nb, cout, 2, device=dev)
+            split = kw.get("split_k", 0)
+            ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev) if split > 1 else None
+            cnt = torch.zeros(8192, device=dev, dtype=torch.int32) if split > 1 else None
+            p = nat.make_igemm_params([x], [cin], nb, h, h, [(0, taps)], wb, cout, out, cout, bias=b, residual=res,
+                                      res_ld=cout, split_k=split, workspace=ws, counters=cnt, stats=st,
+                                      weight_tiled=True, weight_static=True, out2=out2)
+            nat.igemm(p, simple=kw.get("simple", False))
+            torch.cuda.synchronize()
+            xi = x.float().reshape(nb, h, h, cin).permute(0, 3, 1, 2)
+            wq = wt.to(bf).float()
+            if taps == 9:
+                ref = F.conv2d(xi, wq, padding=1).permute(0, 2, 3, 1).reshape(m, cout)
+            else:
+                ref = x.float() @ wq.t()
+            ref = ref + b + res
+            ok &= report(f"igemm f32 stream out {nb}x{h}x{h} {cin}->{cout} taps={taps} {kw}", out, ref, 5e-3)
+            ok &= report("   bf16 shadow", out2, out.to(bf), 0.0)
+            if not kw.get("simple"):
+                o = out.reshape(nb, h * h, cout)
+                ok &= report("   statistics of the f32 values [sum]", st[:, :, 0], o.sum(1), 1e-3)
+                ok &= report("   statistics of the f32 values [sumsq]", st[:, :, 1], (o * o).sum(1), 1e-3)
+        # GroupNorm / LayerNorm reading the f32 stream
+        nb, hw, c0, c1 = 2, 256, 640, 320
+        xs = [torch.randn(nb * hw, c, device=dev) * 1.5 + 0.3 for c in (c0, c1)]
+        sts = [torch.stack([x.reshape(nb, hw, -1).sum(1), (x * x).reshape(nb, hw, -1).sum(1)], dim=-1).contiguous() for x in xs]
+        g, be = torch.randn(c0 + c1, device=dev), torch.randn(c0 + c1, device=dev)
+        y = torch.empty(nb * hw, c0 + c1, device=dev, dtype=bf)
+        nat.groupnorm_apply_cs(xs[0], c0, sts[0], xs[1], c1, sts[1], nb, hw, 32, g, be, 1e-5, True, y)
+        xc = torch.cat(xs, dim=1).reshape(nb, hw, c0 + c1).permute(0, 2, 1)
+        ref = F.silu(F.group_norm(xc, 32, g, be, 1e-5)).permute(0, 2, 1).reshape(nb * hw, c0 + c1)
+        ok &= report("groupnorm apply, f32 sources", y, ref, 1e-2)
+        for (rows, c) in [(4096, 320), (300, 1280)]:
+            x = torch.randn(rows, c, device=dev) + 0.3
+            g, be = torch.randn(c, device=dev), torch.randn(c, device=dev)
+            out = torch.empty(rows, c, device=dev, dtype=bf)
+            nat.layernorm(x, rows, c, g, be, 1e-5, False, out)
+            ok &= report(f"layernorm f32 source rows={rows} c={c}", out, F.layer_norm(x, (c,), g, be, 1e-5), 1e-2)
+    elif group == "xattn":
+        # cross-attention: q [nb*ntok, C], kv [nb*T, 2C]; T = 77 (text) / 257 (CLIP patches) / 1 / 128 (queries)
+        for (nb, ntok, T, heads, d) in [(2, 4096, 77, 8, 40), (2, 1024, 257, 8, 80), (2, 256, 77, 8, 160),
+                                        (2, 64, 77, 8, 160), (1, 1024, 1, 8, 80), (2, 4096, 128, 8, 40),
+                                        (4, 256, 257, 8, 160)]:
+            C = heads * d
+            q = rnd(nb * ntok, C, scale=1.5)
+            kv = rnd(nb * T, 2 * C, scale=1.5)
+            out = torch.full((nb * ntok, C), float("nan"), device=dev, dtype=bf)
+            nat.cross_attention(q, kv, nb, ntok, T, heads, d, out)
+            torch.cuda.synchronize()
+            qq = q.float().reshape(nb, ntok, heads, d).permute(0, 2, 1, 3)
+            kk, vv = kv.float().reshape(nb, T, 2, heads, d).permute(2, 0, 3, 1, 4)
+            ref = F.scaled_dot_product_attention(qq, kk, vv).permute(0, 2, 1, 3).reshape(nb * ntok, C)
+            ok &= report(f"cross-attention nb={nb} ntok={ntok} T={T} heads={heads} d={d}", out, ref, 2e-2)
+    elif group == "sampler":
+        # fused sampler step against the term-by-term formula, all prediction types / clip / guidance / extensions
+        m, n = 2 * 64 * 64, 7
+        coef = torch.rand(n, 4, device=dev) * 0.8 + 0.1
+        sig = torch.rand(n, device=dev) * 0.3
+        for (ptype, clip, cfg, selfc, inpaint, ddpm, step) in [(0, False, False, True, False, False, 3),
+                                                                (1, False, False, True, False, False, 0),
+                                                                (2, True, False, True, False, False, 6),
+                                                                (0, True, True, False, False, False, 2),
+                                                                (0, False, False, True, True, True, 4),
+                                                                (0, False, False, True, True, True, 6)]:
+            eps = torch.randn((2 if cfg else 1) * m, 4, device=dev)
+            lat = torch.randn(m, 4, device=dev)
+            lat0 = lat.clone()
+            x0 = torch.empty(m, 4, device=dev)
+            rgb = torch.randn(m, 4, device=dev)
+            xin = torch.full(((2 if cfg else 1) * m, 16), float("nan"), device=dev, dtype=bf)
+            stp = torch.tensor([step], device=dev, dtype=torch.int32)
+            mask = (torch.rand(m, device=dev) < 0.5).float() if inpaint else None
+            known = torch.randn(n, m, 4, device=dev) if inpaint else None
+            noise = torch.randn(n, m, 4, device=dev) if ddpm else None
+            gs = 7.5
+            nat.sampler_step(eps, lat, x0, rgb, xin, m, coef, stp, n, selfc, mask, known, noise, sig if ddpm else None,
+                             ptype, clip, 0.8, cfg, gs)
+            torch.cuda.synchronize()
+            e = eps[:m] + gs * (eps[m:] - eps[:m]) if cfg else eps
+            sa, sb, pa, pb = coef[step]
+            if ptype == 0:
+                r0, ee = (lat0 - sb * e) / sa, e
+            elif ptype == 1:
+                r0, ee = e, (lat0 - sa * e) / sb
+            else:
+                r0, ee = sa * lat0 - sb * e, sa * e + sb * lat0
+            if clip:
+                r0 = r0.clamp(-0.8, 0.8)
+            pv = pa * r0 + pb * ee
+            last = step == n - 1
+            if ddpm and not last:
+                pv = pv + sig[step] * noise[step]
+            nxt = r0 if last else pv
+            if inpaint:
+                nxt = mask[:, None] * known[step] + (1 - mask[:, None]) * nxt
+            tag = f"sampler_step ptype={ptype} clip={clip} cfg={cfg} inpaint={inpaint} ddpm={ddpm} step={step}"
+            ok &= report(tag + " latents", lat, nxt, 2e-6)
+            ok &= report(tag + " x0", x0, r0, 2e-6)
+            row = torch.cat([lat, rgb, x0 if selfc else torch.zeros_like(x0), torch.zeros(m, 4, device=dev)], 1).to(bf)  # the kernel's own f32 results, rounded
+            ok &= report(tag + " unet_in", xin[:m], row, 0.0)
+            if cfg:
+                ok &= report(tag + " unet_in (second half)", xin[m:], row, 0.0)
+        # select_row / advance_step
+        table = torch.randn(9, 20160, device=dev)
+        stp = torch.tensor([4], device=dev, dtype=torch.int32)
+        dst = torch.empty(3, 20160, device=dev)
+        nat.select_row(table, 20160, stp, 3, dst)
+        nat.advance_step(stp)
+        ok &= report("select_row", dst, table[4:5].expand(3, -1), 0.0)
+        ok &= report("advance_step", stp.float(), torch.tensor([5.0], device=dev), 0.0)
+        # softmax_rows (f32 scores -> bf16 probabilities)
+        for (rows, cols) in [(512, 4096), (128, 16384), (300, 1024)]:
+            sc = torch.randn(rows, cols, device=dev) * 3
+            pr = torch.empty(rows, cols, device=dev, dtype=bf)
+            nat.softmax_rows(sc, rows, cols, 0.044, pr)
+            ok &= report(f"softmax_rows {rows}x{cols}", pr, torch.softmax(sc * 0.044, dim=-1), 1e-2)
+        # add_noise / remove_noise with per-sample device timesteps (+ fused UNet-input write)
+        acp = torch.cumprod(1 - torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, device=dev) ** 2, 0)
+        nb, hw = 3, 32 * 32
+        x = torch.randn(nb, 4, 32, 32, device=dev)
+        nz = torch.randn(nb, 4, 32, 32, device=dev)
+        t = torch.tensor([999, 19, 500], device=dev)
+        out = torch.empty_like(x)
+        xin = torch.zeros(nb * hw, 16, device=dev, dtype=bf)
+        nat.noise_mix(x, nz, t, acp, nb, 4 * hw, 1.0, 0, out, xin, hw, 16)
+        a = acp[t].view(-1, 1, 1, 1)
+        ref = a ** 0.5 * x + (1 - a) ** 0.5 * nz
+        ok &= report("noise_mix add_noise", out, ref, 1e-6)
+        ok &= report("noise_mix add_noise -> unet_in", xin[:, :4], out.permute(0, 2, 3, 1).reshape(-1, 4).to(bf), 0.0)
+        back = torch.empty_like(x)
+        nat.noise_mix(out, nz, t, acp, nb, 4 * hw, 1.0, 1, back)
+        ok &= report("noise_mix remove_noise", back, (ref - (1 - a) ** 0.5 * nz) / a ** 0.5, 1e-5)
+    elif group == "panoptic":
+        # decode tail + post-processing against the transcription of compute_pq (oracle): float stage by agreement,
+        # integer stage (area rules + relabel) bit-exact
+        sys.path.insert(0, ROOT)
+        from oracle import ldmseg_restated as orc
+        import numpy as np
+        g = torch.Generator().manual_seed(3)
+        nb, s = 3, 64
+        base = torch.randn(nb, 128, 8, 8, generator=g) * 4
+        logits = F.interpolate(base, size=(s, s), mode="bilinear") + torch.randn(nb, 128, s, s, generator=g) * 0.3
+        sizes = [(100, 150), (128, 128), (97, 61)]
+        crops = [(0, 0, 2 * s, 2 * s), (0, 0, 2 * s, 100), (8, 4, 96, 120)]
+        cl = logits.permute(0, 2, 3, 1).contiguous().to(dev)
+        geom = torch.tensor([[h, w, *c] for (h, w), c in zip(sizes, crops)], dtype=torch.int32, device=dev)
+        max_hw = max(h * w for h, w in sizes)
+        stride = (max_hw + 15) // 16 * 16
+        pred = torch.full((nb, stride), -7, device=dev, dtype=torch.int16)
+        area = torch.empty(nb, 128, device=dev, dtype=torch.int32)
+        orig = torch.empty(nb, 128, device=dev, dtype=torch.int32)
+        ids = torch.zeros(nb, stride, device=dev, dtype=torch.uint8)
+        keep = torch.empty(nb, 128, device=dev, dtype=torch.int32)
+        count_th, overlap_th = 60, 0.5
+        nat.panoptic_resample(cl, nb, s, 128, 128, geom, max_hw, stride, 0.5, True, pred, area, orig)
+        nat.panoptic_filter(pred, nb, geom, max_hw, stride, area, orig, count_th, overlap_th, 0, ids, keep)
+        torch.cuda.synchronize()
+        up = F.interpolate(logits, scale_factor=2, mode="bilinear", align_corners=False)      # vae.py:270
+        pads = []
+        for (y0, x0, ch, cw) in crops:
+            pm = torch.zeros(2 * s, 2 * s)
+            pm[y0:y0 + ch, x0:x0 + cw] = 1
+            pads.append(pm)
+        ref = orc.panoptic_postprocess(up, sizes, 0.5, count_th, overlap_th, 0, True, padding_masks=pads)
+        for i, (h, w) in enumerate(sizes):
+            got = ids[i, :h * w].view(h, w).cpu().numpy()
+            agree = (got == ref[i][0]).mean()
+            kept = sorted(int(c) + 1 for c in keep[i].nonzero().flatten().cpu())
+            good = agree >= 0.995 and kept == sorted(ref[i][1])
+            print(f"{'PASS' if good else 'FAIL'} panoptic image {i} ({h}x{w}): id agreement {agree:.5f}, segments {len(kept)} vs {len(ref[i][1])}")
+            ok &= bool(good)
+            # integer stage: bit-exact given the kernel's own pred / histograms
+            p_np = pred[i, :h * w].view(h, w).cpu().numpy().astype(np.int64)
+            a_np, o_np = area[i].cpu().numpy(), orig[i].cpu().numpy()
+            assert (np.bincount(p_np[p_np >= 0].ravel(), minlength=128) == a_np).all(), "area histogram"
+            exp_ids, exp_keep = orc.panoptic_filter(p_np, a_np, o_np, None, count_th, overlap_th, 0)
+            exact = (got == exp_ids).all() and kept == exp_keep
+            print(f"{'PASS' if exact else 'FAIL'} panoptic image {i}: integer stage bit-exact")
+            ok &= bool(exact)
+    elif group == "vae_pdl":
+        # the AutoencoderKL mid-block attention feeds tensors produced on the stream as igemm "weights": under PDL
+        # they must not be fetched before the grid-dependency wait.  Encoder at 128 / 256 px, PDL on (many
+        # repetitions) vs PDL off.
+        from ldmseg.models import GeneralVAEImage
+        from ldmseg.engine import plan as plan_mod
+        torch.manual_seed(0)
+        vae = GeneralVAEImage().to(dev)
+        for size, nb in ((128, 2), (256, 1)):
+            x = torch.rand(nb, 3, size, size, device=dev) * 2 - 1
+            eng = vae._get_engine()
+            pl = eng.plan(nb, size)
+            pl.pdl = False
+            ref = eng.encode(x).clone()
+            pl.pdl = True
+            worst = 0.0
+            for _ in range(20):
+                out = eng.encode(x)
+                worst = max(worst, ((out - ref).norm() / ref.norm()).item())
+            good = worst < 2e-3
+            print(f"{'PASS' if good else 'FAIL'} VAE encoder {size}px nb={nb}: PDL vs no-PDL worst rel_l2 over 20 runs = {worst:.3e}")
+            ok &= good
     torch.cuda.synchronize()
     print(f"GROUP {group}: {'OK' if ok else 'FAILED'}", flush=True)
     return ok
