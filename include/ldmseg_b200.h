@@ -112,6 +112,16 @@ typedef struct ldmseg_igemm_params {
                                         TMA traversal stride (diffusers Downsample2D, unet.py:361-373; the
                                         AutoencoderKL encoder's F.pad(0,1,0,1) + stride-2 conv) */
   int conv_pad;                      /* stride 2 only: zero padding before (top / left): 1 (UNet) or 0 (VAE) */
+  /* LayerNorm folded into the GEMMs on either side of it (BasicTransformerBlock.norm1 / norm3 feed to_q/k/v and
+   * ff.net.0.proj): the PRODUCER of the row x accumulates its per-row moments, the CONSUMER multiplies the raw x by
+   * W' = W diag(gamma) and finishes  out = rstd_m * (acc - mean_m * colsum[n]) + bias[n],  bias = W beta + b,
+   * colsum[n] = sum_k W'[n, k] (of the bf16-rounded W').  One launch per LayerNorm disappears. */
+  float* rowstats_out;               /* producer: f32 [M, 2] += per-row {sum, sum of squares} of the stored bf16
+                                        output (of the bf16 shadow `out2` for an f32 out); caller zeroes it */
+  const float* ln_rowstats;          /* consumer: the producer's [M, 2] */
+  const float* ln_colsum;            /* consumer: f32 [n] */
+  int ln_channels;                   /* consumer: row width C of the LayerNorm (mean = sum / C) */
+  float ln_eps;
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);

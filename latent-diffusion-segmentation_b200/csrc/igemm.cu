@@ -67,6 +67,11 @@ struct alignas(64) IgemmKParams {
   int* counters;
   float* stats;       // optional per-(image, channel) {sum, sum of squares} of the stored output
   int stats_hw;       // rows per image for the statistics (the producer may be a plain [M, K] GEMM)
+  float* rowstats;            // optional [M, 2]: += per-row {sum, sum of squares} of the stored bf16 output (LayerNorm
+                              // statistics for a consumer GEMM that folds the LayerNorm)
+  const float* ln_rowstats;   // LayerNorm folded into THIS GEMM: A is the un-normalised row x, the weights carry gamma,
+  const float* ln_colsum;     // out = rstd_m * (acc - mean_m * colsum[n]) + bias[n]   (bias carries W beta + b)
+  float ln_inv_c, ln_eps;
   int w_tiled;        // weights stored as [N/16][K/64][16][64] blocks (2 KB contiguous per block)
   int prefetch_b;     // issue the first work item's weight loads before the grid-dependency wait
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
@@ -142,6 +147,10 @@ __device__ __forceinline__ float2 fast_gelu2(float2 x) {
 // made every access a load the compiler had to repeat after each global store).
 struct EpiArgs {
   int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw, vec_ok, res_f32, out2_ld;
+  float ln_inv_c, ln_eps;
+  float* rowstats;
+  const float* ln_rowstats;
+  const float* ln_colsum;
   const float* bias;
   const float* rowbias;
   const void* residual;
@@ -166,12 +175,25 @@ __device__ __forceinline__ float warp_column_sums(float (&a)[32], int lane) {
 }
 
 // Finish one 32-column chunk: v[i] = accumulator of (row m, column col0 + i).
+// ln_mu / ln_r: LayerNorm statistics of this row when the LayerNorm is folded into this GEMM; rs1 / rs2 accumulate
+// the row's {sum, sum of squares} of the stored bf16 values for a LayerNorm folded into the NEXT GEMM.
 template <bool GEGLU>
 __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int m, int img, int img_stats,
-                                           int col0, int lane) {
+                                           int col0, int lane, float ln_mu, float ln_r, float& rs1, float& rs2) {
   const bool row_ok = m < p.M;
   const bool full = (col0 + 32 <= p.N) && p.vec_ok;
   if (full) {
+    if (p.ln_colsum != nullptr) {
+      const float nmr = -ln_mu * ln_r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
+        v[4 * j] = fmaf(ln_r, v[4 * j], nmr * s4.x);
+        v[4 * j + 1] = fmaf(ln_r, v[4 * j + 1], nmr * s4.y);
+        v[4 * j + 2] = fmaf(ln_r, v[4 * j + 2], nmr * s4.z);
+        v[4 * j + 3] = fmaf(ln_r, v[4 * j + 3], nmr * s4.w);
+      }
+    }
     if (p.bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -242,6 +264,14 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
             __nv_bfloat16* o2 = p.out2 + static_cast<size_t>(m) * p.out2_ld + col0;
             stg256(o2, o0);
             stg256(o2 + 16, o1);
+            if (p.rowstats != nullptr) {   // of the bf16 shadow: that is what the folding GEMM multiplies
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 a = unpack_bf16x2(o0[i]), b = unpack_bf16x2(o1[i]);
+                rs1 += (a.x + a.y) + (b.x + b.y);
+                rs2 += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
+              }
+            }
           }
         }
       } else {
@@ -256,11 +286,18 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
           stg256(op, o0);
           stg256(op + 16, o1);
         }
-        if (p.stats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
+        if (p.stats != nullptr || p.rowstats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float2 a = unpack_bf16x2(o0[i]), b = unpack_bf16x2(o1[i]);
             v[2 * i] = a.x; v[2 * i + 1] = a.y; v[16 + 2 * i] = b.x; v[17 + 2 * i] = b.y;
+          }
+          if (p.rowstats != nullptr && row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              rs1 += v[i];
+              rs2 = fmaf(v[i], v[i], rs2);
+            }
           }
         }
       }
@@ -277,6 +314,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
     for (int i = 0; i < ncol; ++i) {
       const int col = col0 + i;
       float x = tmp[i];
+      if (p.ln_colsum != nullptr) x = ln_r * (x - ln_mu * __ldg(p.ln_colsum + col));
       if (p.bias != nullptr) x += __ldg(p.bias + col);
       if (rb != nullptr) x += __ldg(rb + col);
       if (p.residual != nullptr)
@@ -291,6 +329,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
         const __nv_bfloat16 o = __float2bfloat16(x);
         reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = o;
         x = __bfloat162float(o);
+      }
+      if (p.rowstats != nullptr) {
+        const float xb = __bfloat162float(__float2bfloat16(x));
+        rs1 += xb;
+        rs2 = fmaf(xb, xb, rs2);
       }
       tmp[i] = x;
     }
@@ -330,6 +373,14 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
   const int row_in_tile = q * 32 + lane;
   const int img = m / p.HW;                                       // image of this row (per-image bias)
   const int img_stats = MODE == EPI_PARTIAL ? 0 : m_base / p.stats_hw;  // image of the warp's rows (statistics)
+  float ln_mu = 0.f, ln_r = 1.f, rs1 = 0.f, rs2 = 0.f;
+  if constexpr (MODE != EPI_PARTIAL) {
+    if (p.ln_rowstats != nullptr && m < p.M) {
+      const float2 rs = __ldcg(reinterpret_cast<const float2*>(p.ln_rowstats) + m);
+      ln_mu = rs.x * p.ln_inv_c;
+      ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, rs.y * p.ln_inv_c), 0.f) + p.ln_eps);
+    }
+  }
 #pragma unroll 1
   for (int ch = half; ch < kChunks; ch += NH) {
     const int col0 = n0 + ch * 32;
@@ -364,7 +415,13 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     }
-    epi_finish<GEGLU>(p, v, m, img, img_stats, col0, lane);
+    epi_finish<GEGLU>(p, v, m, img, img_stats, col0, lane, ln_mu, ln_r, rs1, rs2);
+  }
+  if constexpr (MODE != EPI_PARTIAL && !GEGLU) {
+    if (p.rowstats != nullptr && m < p.M) {
+      atomicAdd(p.rowstats + 2 * static_cast<size_t>(m), rs1);
+      atomicAdd(p.rowstats + 2 * static_cast<size_t>(m) + 1, rs2);
+    }
   }
 }
 
@@ -610,6 +667,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     ea.stats_hw = p.stats_hw; ea.vec_ok = p.vec_ok; ea.bias = p.bias; ea.rowbias = p.rowbias;
     ea.residual = p.residual; ea.out = p.out; ea.stats = p.stats;
     ea.res_f32 = p.res_f32; ea.out2 = p.out2; ea.out2_ld = p.out2_ld;
+    ea.rowstats = p.rowstats; ea.ln_rowstats = p.ln_rowstats; ea.ln_colsum = p.ln_colsum;
+    ea.ln_inv_c = p.ln_inv_c; ea.ln_eps = p.ln_eps;
     const uint32_t tmem_empty0 = PAIR ? map_to_cta(&tmem_empty[0], 0) : 0u;   // the leader's barrier
     auto release_acc = [&](int acc) {
       if constexpr (PAIR) mbar_arrive_cluster(tmem_empty0 + acc * 8);
@@ -735,6 +794,11 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
     }
   }
   // epilogue identical to the tcgen05 kernel (GEGLU handled by the pair thread layout below)
+  if (p.ln_colsum) {
+    const float mu = p.ln_rowstats[2 * static_cast<size_t>(m)] / static_cast<float>(p.ln_channels);
+    const float var = fmaxf(p.ln_rowstats[2 * static_cast<size_t>(m) + 1] / static_cast<float>(p.ln_channels) - mu * mu, 0.f);
+    acc = rsqrtf(var + p.ln_eps) * (acc - mu * p.ln_colsum[n]);
+  }
   if (p.bias) acc += p.bias[n];
   if (p.rowbias) acc += p.rowbias[static_cast<size_t>(b) * p.rowbias_ld + n];
   if (p.act == LDMSEG_ACT_GEGLU) {
@@ -762,6 +826,11 @@ __global__ void igemm_simple_kernel(ldmseg_igemm_params p, int M, int HW) {
     const __nv_bfloat16 o = __float2bfloat16(acc);
     reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + n] = o;
     acc = __bfloat162float(o);
+  }
+  if (p.rowstats_out) {
+    const float xb = __bfloat162float(__float2bfloat16(acc));
+    atomicAdd(p.rowstats_out + 2 * static_cast<size_t>(m), xb);
+    atomicAdd(p.rowstats_out + 2 * static_cast<size_t>(m) + 1, xb * xb);
   }
   if (p.stats) {
     const int sb = p.stats_hw > 0 ? m / p.stats_hw : b;
@@ -821,6 +890,12 @@ static int validate(const ldmseg_igemm_params* p) {
   if (p->out2) {
     LDM_REQUIRE(p->out_dtype == LDMSEG_OUT_F32 && p->act != LDMSEG_ACT_GEGLU, "igemm: out2 (bf16 shadow) needs an f32 out");
     LDM_REQUIRE(p->out2_ld % 4 == 0, "igemm: out2_ld must be a multiple of 4");
+  }
+  if (p->rowstats_out) LDM_REQUIRE(p->act != LDMSEG_ACT_GEGLU, "igemm: rowstats_out is not defined for GEGLU");
+  if (p->ln_colsum || p->ln_rowstats) {
+    LDM_REQUIRE(p->ln_colsum && p->ln_rowstats && p->ln_channels > 0, "igemm: a folded LayerNorm needs ln_rowstats, ln_colsum and ln_channels");
+    LDM_REQUIRE((reinterpret_cast<uintptr_t>(p->ln_colsum) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->ln_rowstats) & 7) == 0,
+                "igemm: ln_colsum / ln_rowstats misaligned");
   }
   if (p->next_weight) LDM_REQUIRE((reinterpret_cast<uintptr_t>(p->next_weight) & 15) == 0, "igemm: next_weight misaligned");
   if (p->rowbias) LDM_REQUIRE(p->rowbias_ld % 4 == 0, "igemm: rowbias_ld must be a multiple of 4");
@@ -1023,6 +1098,11 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     kp.counters = p->tile_counters;
   }
   kp.stats = p->stats;
+  kp.rowstats = p->rowstats_out;
+  kp.ln_rowstats = p->ln_rowstats;
+  kp.ln_colsum = p->ln_colsum;
+  kp.ln_inv_c = p->ln_channels > 0 ? 1.f / static_cast<float>(p->ln_channels) : 0.f;
+  kp.ln_eps = p->ln_eps;
   kp.debug = g_debug;
   kp.w_tiled = p->weight_tiled;
   {

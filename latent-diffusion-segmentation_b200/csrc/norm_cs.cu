@@ -39,7 +39,8 @@ __device__ __forceinline__ float silu_1mufu(float t) {
 }
 
 // SRC_F32: both sources are f32 (the fp32 residual stream); otherwise bf16.
-template <int UNROLL, bool SRC_F32>
+// HOIST: issue the first trip's loads before the statistics phase (small batches: latency; costs ~20 registers)
+template <int UNROLL, bool SRC_F32, bool HOIST>
 __global__ void __launch_bounds__(512)
 gn_apply_cs_kernel(const void* __restrict__ s0v, int c0, const float* __restrict__ cs0,
                    const void* __restrict__ s1v, int c1, const float* __restrict__ cs1, int hw,
@@ -66,6 +67,34 @@ gn_apply_cs_kernel(const void* __restrict__ s0v, int c0, const float* __restrict
     be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
   }
   pdl_sync();
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  const bool from0 = ch < c0;
+  using src_t = typename std::conditional<SRC_F32, float, __nv_bfloat16>::type;
+  const src_t* s0 = reinterpret_cast<const src_t*>(s0v);
+  const src_t* s1 = reinterpret_cast<const src_t*>(s1v);
+  const src_t* src = from0 ? s0 + static_cast<size_t>(b) * hw * c0 + ch
+                           : s1 + static_cast<size_t>(b) * hw * c1 + (ch - c0);
+  const int sld = from0 ? c0 : c1;
+  __nv_bfloat16* dst = out + static_cast<size_t>(b) * hw * C + ch;
+  constexpr int kVec = SRC_F32 ? 2 : 1;   // 16-byte vectors per octet
+  // The first trip's activation loads do not depend on the statistics: issue them now, so that their L2 round trip
+  // overlaps the one of the moments below (at batch 1 a thread makes exactly one trip: the whole kernel then costs
+  // one round trip instead of two).
+  uint4 u[UNROLL][kVec];
+  int p0 = idle ? p_end : p_begin + plane;
+  auto load_trip = [&](int pbase) {
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const int p = pbase + k * lanes;
+      if (p < p_end) {
+#pragma unroll
+        for (int v = 0; v < kVec; ++v)
+          u[k][v] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * sld) + v);
+      }
+    }
+  };
+  if constexpr (HOIST) load_trip(p0);
   // group moments from the producer's channel moments: one warp per group, several groups per warp.  All loads of
   // a warp's groups are issued before the first reduction, so the phase costs ONE L2 round trip instead of one per
   // group.  (Shared-memory float atomics -- one channel per thread -- were tried and cost 10 us per launch inside
@@ -115,28 +144,8 @@ gn_apply_cs_kernel(const void* __restrict__ s0v, int c0, const float* __restrict
     sc[i] = ga[i] * gstat[2 * g + 1];
     sh[i] = be[i] - gstat[2 * g] * sc[i];
   }
-  const int p_begin = blockIdx.x * pix_per_cta;
-  const int p_end = min(hw, p_begin + pix_per_cta);
-  const bool from0 = ch < c0;
-  using src_t = typename std::conditional<SRC_F32, float, __nv_bfloat16>::type;
-  const src_t* s0 = reinterpret_cast<const src_t*>(s0v);
-  const src_t* s1 = reinterpret_cast<const src_t*>(s1v);
-  const src_t* src = from0 ? s0 + static_cast<size_t>(b) * hw * c0 + ch
-                           : s1 + static_cast<size_t>(b) * hw * c1 + (ch - c0);
-  const int sld = from0 ? c0 : c1;
-  __nv_bfloat16* dst = out + static_cast<size_t>(b) * hw * C + ch;
-  constexpr int kVec = SRC_F32 ? 2 : 1;   // 16-byte vectors per octet
-  for (int p0 = idle ? p_end : p_begin + plane; p0 < p_end; p0 += lanes * UNROLL) {
-    uint4 u[UNROLL][kVec];
-#pragma unroll
-    for (int k = 0; k < UNROLL; ++k) {
-      const int p = p0 + k * lanes;
-      if (p < p_end) {
-#pragma unroll
-        for (int v = 0; v < kVec; ++v)
-          u[k][v] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * sld) + v);
-      }
-    }
+  while (p0 < p_end) {
+    if constexpr (!HOIST) load_trip(p0);
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
       const int p = p0 + k * lanes;
@@ -162,6 +171,8 @@ gn_apply_cs_kernel(const void* __restrict__ s0v, int c0, const float* __restrict
       o.w = pack_bf16x2(f[6], f[7]);
       *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p) * C) = o;
     }
+    p0 += lanes * UNROLL;
+    if constexpr (HOIST) load_trip(p0);
   }
 }
 
@@ -197,13 +208,13 @@ static int gn_apply_cs_launch(const void* src0, int c0, const float* chan_stats0
   const bool deep = ppc >= 16 * lanes;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (src_f32)
-    launch_kernel(gn_apply_cs_kernel<4, true>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
+    launch_kernel(gn_apply_cs_kernel<4, true, true>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
                   src1, c1, chan_stats1, hw, ppc, groups, gamma, beta, eps, silu, o);
   else if (deep)
-    launch_kernel(gn_apply_cs_kernel<8, false>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
+    launch_kernel(gn_apply_cs_kernel<8, false, false>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
                   src1, c1, chan_stats1, hw, ppc, groups, gamma, beta, eps, silu, o);
   else
-    launch_kernel(gn_apply_cs_kernel<4, false>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
+    launch_kernel(gn_apply_cs_kernel<4, false, true>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
                   src1, c1, chan_stats1, hw, ppc, groups, gamma, beta, eps, silu, o);
   return check_launch("gn_apply_cs_kernel");
 }

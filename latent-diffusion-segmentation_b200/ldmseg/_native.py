@@ -74,6 +74,11 @@ class IgemmParams(C.Structure):
         ("out2_ld", C.c_int),
         ("conv_stride", C.c_int),
         ("conv_pad", C.c_int),
+        ("rowstats_out", C.c_void_p),
+        ("ln_rowstats", C.c_void_p),
+        ("ln_colsum", C.c_void_p),
+        ("ln_channels", C.c_int),
+        ("ln_eps", C.c_float),
     ]
 
 
@@ -177,7 +182,9 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       counters: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
                       stats_hw: int = 0, pdl: bool = False, weight_tiled: bool = False,
                       pair: bool = False, weight_static: bool = False, out2: Optional[torch.Tensor] = None,
-                      conv_stride: int = 1, conv_pad: int = 1) -> IgemmParams:
+                      conv_stride: int = 1, conv_pad: int = 1, rowstats_out: Optional[torch.Tensor] = None,
+                      ln_rowstats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None,
+                      ln_channels: int = 0, ln_eps: float = 0.0) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -221,6 +228,11 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.out2_ld = out2.shape[1] if out2 is not None else 0
     p.conv_stride = conv_stride
     p.conv_pad = conv_pad
+    p.rowstats_out = _ptr(rowstats_out)
+    p.ln_rowstats = _ptr(ln_rowstats)
+    p.ln_colsum = _ptr(ln_colsum)
+    p.ln_channels = ln_channels
+    p.ln_eps = ln_eps
     return p
 
 

@@ -90,6 +90,19 @@ def pack_convT2x2(w: torch.Tensor, b: torch.Tensor):
     return pack_linear(wt), b.float().repeat(4)
 
 
+def fold_layernorm(w: torch.Tensor, b, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm folded into the Linear that consumes it:  LN(x) W^T + b  =  rstd (x W'^T - mean * colsum) + c  with
+    W' = W diag(gamma), c = W beta + b and colsum[n] = sum_k W'[n, k] taken over the bf16-ROUNDED W' (so that the mean
+    term cancels exactly what the tensor cores accumulate).  Returns (W' f32, c f32, colsum f32)."""
+    w = w.detach().float()
+    wf = w * gamma.detach().float()[None, :]
+    c = w @ beta.detach().float()
+    if b is not None:
+        c = c + b.detach().float()
+    colsum = wf.to(torch.bfloat16).float().sum(dim=1)
+    return wf, c, colsum
+
+
 def to_bf16(w: torch.Tensor) -> torch.Tensor:
     return w.to(torch.bfloat16).contiguous()
 

@@ -27,6 +27,9 @@ RESID_F32 = os.environ.get("LDMSEG_RESID_F32", "0") != "0"
 # each igemm launch pulls the NEXT launch's weights into L2 while its own tail runs (weight streaming at small
 # batch); only below this many output rows per forward level-0 launch (large batches are compute-bound)
 NEXTW_MAX_ROWS = int(os.environ.get("LDMSEG_NEXTW_MAX_ROWS", "8192"))
+# LayerNorm folded into the GEMMs around it (row moments from the producer's epilogue, gamma / beta in the consumer's
+# weights): one launch per LayerNorm less (32 per UNet forward); 0 = separate LayerNorm kernels
+LN_FOLD = os.environ.get("LDMSEG_LN_FOLD", "1") != "0"
 
 
 USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
@@ -186,7 +189,9 @@ class PlanBase:
         self._f32: Dict[int, torch.Tensor] = {}     # bf16 handle ptr -> f32 tensor of the residual stream
         self._igemm_params: list = []
         self.gn_stats = torch.zeros(nb * 64 * 2, device=self.device, dtype=torch.float32)
-        self.stats_arena = torch.zeros(nb * 512 * 1024, device=self.device, dtype=torch.float32)
+        # per-(image, channel) GroupNorm moments and per-row LayerNorm moments written by producer epilogues; one
+        # memset per run
+        self.stats_arena = torch.zeros(nb * 1024 * 1024, device=self.device, dtype=torch.float32)
         self._arena_used = 0
         self._producer: Dict[int, tuple] = {}   # out.data_ptr() -> (IgemmParams, n, rows_per_image)
         self._chan_stats: Dict[int, torch.Tensor] = {}
@@ -207,7 +212,7 @@ class PlanBase:
 
     def _gemm(self, layer: _Layer, srcs, src_c, nb, h, w, segs, out, *, rowbias=None, residual=None,
               act=nat.ACT_NONE, out_ld=None, bias="layer", allow_split=True, stream=False, shadow=True,
-              conv_stride=1, conv_pad=1):
+              conv_stride=1, conv_pad=1, rowstats=None, ln=None):
         """Append one igemm launch.  `stream=True` marks `out` as a tensor of the residual stream: under
         RESID_F32 it is written as f32 (+ a bf16 shadow in `out` when `shadow`), and later `residual=` /
         GroupNorm / LayerNorm reads of `out` use the f32 copy."""
@@ -234,7 +239,10 @@ class PlanBase:
                                   act=act, block_n=bn, split_k=split, workspace=self.ws, counters=self.counters,
                                   pdl=self.pdl, weight_tiled=tiled, pair=pair,
                                   weight_static=bool(layer.extra.get("static", False)), out2=out2,
-                                  conv_stride=conv_stride, conv_pad=conv_pad)
+                                  conv_stride=conv_stride, conv_pad=conv_pad, rowstats_out=rowstats,
+                                  ln_rowstats=None if ln is None else ln[0],
+                                  ln_colsum=None if ln is None else layer.extra["ln_colsum"],
+                                  ln_channels=0 if ln is None else ln[1], ln_eps=0.0 if ln is None else ln[2])
         self._keep.append(p)
         self._igemm_params.append((p, layer, m))
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
@@ -271,6 +279,13 @@ class PlanBase:
                 continue
             p.next_weight = nxt.w.data_ptr()
             p.next_weight_bytes = nbytes
+
+    def _arena(self, n: int) -> Optional[torch.Tensor]:
+        if self._arena_used + n > self.stats_arena.numel():
+            return None
+        sl = self.stats_arena[self._arena_used:self._arena_used + n]
+        self._arena_used += n
+        return sl
 
     def _stats_for(self, src, c, hw) -> Optional[torch.Tensor]:
         """Channel-statistics slice for a GroupNorm source written by an igemm of this plan (or None)."""

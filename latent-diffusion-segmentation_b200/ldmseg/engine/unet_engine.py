@@ -23,7 +23,7 @@ import torch
 
 from ldmseg import _native as nat
 from ldmseg import _pack as pk
-from .plan import PlanBase, WeightsBase
+from .plan import LN_FOLD, PlanBase, WeightsBase
 
 
 class UNetWeights(WeightsBase):
@@ -65,11 +65,22 @@ class UNetWeights(WeightsBase):
         self._norm(name + ".ln3", blk.norm3)
         a = blk.attn1
         wqkv = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], dim=0)
-        self._gemm(name + ".qkv", pk.pack_linear(wqkv), None, 3 * c)
+        w1, b1 = blk.ff.net[0].proj.weight.detach().float(), blk.ff.net[0].proj.bias.detach().float()
+        if LN_FOLD:
+            # norm1 -> to_q/k/v and norm3 -> ff.net.0.proj: the LayerNorm lives in the consumer's weights / epilogue
+            wq, cq, sq = pk.fold_layernorm(wqkv, None, blk.norm1.weight, blk.norm1.bias)
+            self._gemm(name + ".qkv", pk.pack_linear(wq), cq, 3 * c, ln_colsum=self._dev(sq),
+                       ln_eps=float(blk.norm1.eps))
+            wf, cf, _ = pk.fold_layernorm(w1, b1, blk.norm3.weight, blk.norm3.bias)
+            wi, bi = pk.interleave_geglu(wf, cf)
+            si = wi.to(torch.bfloat16).float().sum(dim=1)
+            self._gemm(name + ".ff1", pk.pack_linear(wi), bi, wi.shape[0], ln_colsum=self._dev(si),
+                       ln_eps=float(blk.norm3.eps))
+        else:
+            self._gemm(name + ".qkv", pk.pack_linear(wqkv), None, 3 * c)
+            wi, bi = pk.interleave_geglu(w1, b1)
+            self._gemm(name + ".ff1", pk.pack_linear(wi), bi, wi.shape[0])
         self._gemm(name + ".to_out", pk.pack_linear(a.to_out[0].weight), a.to_out[0].bias, c)
-        wi, bi = pk.interleave_geglu(blk.ff.net[0].proj.weight.detach().float(),
-                                     blk.ff.net[0].proj.bias.detach().float())
-        self._gemm(name + ".ff1", pk.pack_linear(wi), bi, wi.shape[0])
         self._gemm(name + ".ff2", pk.pack_linear(blk.ff.net[2].weight), blk.ff.net[2].bias, c)
         self._gemm(name + ".proj_out", pk.pack_linear(t.proj_out.weight), t.proj_out.bias, c)
 
@@ -190,17 +201,31 @@ class UNetPlan(PlanBase):
         d = c // heads
         g = self._buf(m, c)
         self._gn(name + ".norm", x, c, None, 0, hw, False, g)
+        fold = "ln_colsum" in W.L[name + ".qkv"].extra
         t0 = self._buf(m, c)
-        self._gemm(W.L[name + ".proj_in"], [g], [c], 1, 1, m, [(0, 1)], t0, stream=True)
-        ln = self._buf(m, c)
-        self._ln(name + ".ln1", t0, m, c, ln)
+        rs0 = self._arena(2 * m) if fold else None
+        if fold and rs0 is None:
+            raise RuntimeError("statistics arena exhausted: the LayerNorm-folded weights cannot run without row moments")
+        self._gemm(W.L[name + ".proj_in"], [g], [c], 1, 1, m, [(0, 1)], t0, stream=True, rowstats=rs0)
         qkv = self._buf(m, 3 * c)
-        self._gemm(W.L[name + ".qkv"], [ln], [c], 1, 1, m, [(0, 1)], qkv)
+        if fold:
+            # norm1 folded: the GEMM multiplies the raw row, its epilogue applies mean / rstd from proj_in's moments
+            self._gemm(W.L[name + ".qkv"], [t0], [c], 1, 1, m, [(0, 1)], qkv,
+                       ln=(rs0, c, W.L[name + ".qkv"].extra["ln_eps"]))
+        else:
+            ln = self._buf(m, c)
+            self._ln(name + ".ln1", t0, m, c, ln)
+            self._gemm(W.L[name + ".qkv"], [ln], [c], 1, 1, m, [(0, 1)], qkv)
         ao = self._buf(m, c)
         self._op(lambda: nat.attention(qkv, nb, hw, heads, d, ao), tag=f"attn:{m}:{name}")
         t1 = self._buf(m, c)
-        self._gemm(W.L[name + ".to_out"], [ao], [c], 1, 1, m, [(0, 1)], t1, residual=t0, stream=True)
-        if name in W.cross_layers:
+        has_x = name in W.cross_layers
+        rs1 = self._arena(2 * m) if fold else None
+        if fold and rs1 is None:
+            raise RuntimeError("statistics arena exhausted: the LayerNorm-folded weights cannot run without row moments")
+        self._gemm(W.L[name + ".to_out"], [ao], [c], 1, 1, m, [(0, 1)], t1, residual=t0, stream=True,
+                   rowstats=None if has_x else rs1)
+        if has_x:
             # h = attn2(norm2(h), encoder_hidden_states) + h; K / V of the (step-invariant) encoder states are
             # produced once per call by `set_encoder_hidden_states`, outside the per-step launch list
             T = self.ntok_enc
@@ -220,12 +245,17 @@ class UNetPlan(PlanBase):
             ax = self._buf(m, c)
             self._op(lambda: nat.cross_attention(qx, kv, nb, hw, T, heads, d, ax), tag=f"xattn:{m}:{name}")
             t1b = self._buf(m, c)
-            self._gemm(W.L[name + ".to_out2"], [ax], [c], 1, 1, m, [(0, 1)], t1b, residual=t1, stream=True)
+            self._gemm(W.L[name + ".to_out2"], [ax], [c], 1, 1, m, [(0, 1)], t1b, residual=t1, stream=True,
+                       rowstats=rs1)
             t1 = t1b
-        ln2 = self._buf(m, c)
-        self._ln(name + ".ln3", t1, m, c, ln2)
         ff = self._buf(m, 4 * c)
-        self._gemm(W.L[name + ".ff1"], [ln2], [c], 1, 1, m, [(0, 1)], ff, act=nat.ACT_GEGLU)
+        if fold:
+            self._gemm(W.L[name + ".ff1"], [t1], [c], 1, 1, m, [(0, 1)], ff, act=nat.ACT_GEGLU,
+                       ln=(rs1, c, W.L[name + ".ff1"].extra["ln_eps"]))
+        else:
+            ln2 = self._buf(m, c)
+            self._ln(name + ".ln3", t1, m, c, ln2)
+            self._gemm(W.L[name + ".ff1"], [ln2], [c], 1, 1, m, [(0, 1)], ff, act=nat.ACT_GEGLU)
         t2 = self._buf(m, c)
         self._gemm(W.L[name + ".ff2"], [ff], [4 * c], 1, 1, m, [(0, 1)], t2, residual=t1)
         out = self._buf(m, c)
@@ -303,7 +333,11 @@ class UNetPlan(PlanBase):
 
 
 class UNetEngine:
+    _serial = 0
+
     def __init__(self, unet):
+        UNetEngine._serial += 1
+        self.serial = UNetEngine._serial      # identity for caches keyed on "this set of packed weights" (id() is reused)
         dev = next(unet.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("ldmseg_b200: UNet must live on a CUDA device (no CPU fallback); call .to('cuda')")

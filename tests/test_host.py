@@ -32,7 +32,7 @@ def test_igemm_params_struct_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_0-9]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
     fields = [f[0] for f in nat.IgemmParams._fields_]
-    assert fields == names and len(fields) == 39
+    assert fields == names and len(fields) == 44
 
 
 def test_product_scheduler_host_logic_matches_reference(golden_dir):
@@ -167,3 +167,48 @@ def test_tuned_tiling_table_is_legal():
         assert us_tuned < us_model
         assert plan.choose_tiling(m, n, kb, allow_pair=True) == (bn, split, bool(pair))
         assert plan.choose_tiling(m, n, kb, allow_pair=True, use_tuned=False) != (bn, split, bool(pair))
+
+
+def test_layernorm_fold_algebra():
+    """pk.fold_layernorm: LN(x) W^T + b == rstd * (x W'^T - mean * colsum) + c (host logic of the folded launch)."""
+    import torch.nn.functional as F
+    from ldmseg import _pack as pk
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(37, 320, generator=g) * 1.7 + 0.4).double()
+    w, b = torch.randn(96, 320, generator=g).double(), torch.randn(96, generator=g).double()
+    gam, bet = torch.randn(320, generator=g).double() * 0.3 + 1, torch.randn(320, generator=g).double() * 0.2
+    ref = F.layer_norm(x, (320,), gam, bet, 1e-5) @ w.t() + b
+    wf, c, colsum = pk.fold_layernorm(w.float(), b.float(), gam.float(), bet.float())
+    mu = x.mean(1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    got = rstd * (x @ wf.double().t() - mu * wf.double().sum(1)[None]) + c.double()[None]
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    # colsum is taken over the bf16-rounded weights: the mean term then cancels what the tensor cores accumulate
+    torch.testing.assert_close(colsum, wf.to(torch.bfloat16).float().sum(1))
+    # GEGLU interleave commutes with the fold
+    wi, bi = pk.interleave_geglu(wf[:64], c[:64])
+    assert wi.shape == (64, 320) and torch.equal(wi[:16], wf[:16]) and torch.equal(wi[16:32], wf[32:48])
+
+
+def test_descriptor_variants_configure_the_unet():
+    """descriptors.py:67-105: 'learnable' adds queries, 'clip_image' adds the 1024->768 projection; both keep
+    cross-attention (the engine then needs encoder_hidden_states)."""
+    from ldmseg.models import UNet
+    from ldmseg.models import descriptors as D
+    from oracle.make_golden import TINY
+    unet = UNet(**TINY)
+    assert D.get_image_descriptor_model("learnable", None, unet) == (None, None, None)
+    assert tuple(unet.object_queries.weight.shape) == (128, 768)
+    unet2 = UNet(**TINY)
+    unet2.modify_encoder_hidden_state_proj(1024, 768)
+    assert tuple(unet2.encoder_hid_proj.weight.shape) == (768, 1024)
+    assert any(tb.attn2 is not None for b in unet2.down_blocks if hasattr(b, "attentions")
+               for a in b.attentions for tb in a.transformer_blocks)
+    # a tiny CLIP vision tower from config (no network): last_feat is [B, D, T] as the reference's wrapper returns
+    m = D.make_vision_descriptor(False, name="", hidden_size=32, intermediate_size=64, num_hidden_layers=1,
+                                 num_attention_heads=2, image_size=224, patch_size=56, projection_dim=16)
+    enc = D.image_descriptors(m.eval(), torch.rand(2, 3, 40, 40))
+    assert enc.shape[0] == 4 and enc.shape[2] == 32
+    mp = D.make_vision_descriptor(True, name="", hidden_size=32, intermediate_size=64, num_hidden_layers=1,
+                                  num_attention_heads=2, image_size=224, patch_size=56, projection_dim=16)
+    assert tuple(D.image_descriptors(mp.eval(), torch.rand(1, 3, 40, 40)).shape) == (2, 1, 16)

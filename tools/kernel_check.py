@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_pair", "igemm_s2", "igemm_f32stream",
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_pair", "igemm_s2", "igemm_f32stream", "igemm_lnfold",
           "gn_fused", "norm", "attn_simple", "attn", "xattn", "elementwise", "sampler", "panoptic", "vae_pdl"]
 
 
@@ -457,6 +457,51 @@ def run_group(group):
             out = torch.empty(rows, c, device=dev, dtype=bf)
             nat.layernorm(x, rows, c, g, be, 1e-5, False, out)
             ok &= report(f"layernorm f32 source rows={rows} c={c}", out, F.layer_norm(x, (c,), g, be, 1e-5), 1e-2)
+    elif group == "igemm_lnfold":
+        # LayerNorm folded into the GEMMs around it: the producer accumulates per-row moments of its bf16 output, the
+        # consumer multiplies the raw rows by W diag(gamma) and finishes rstd * (acc - mean * colsum) + (W beta + b)
+        for (m, c, n, kw) in [(4096, 320, 960, {}), (1024, 640, 5120, dict(geglu=True)), (256, 1280, 10240, dict(geglu=True)),
+                              (64, 1280, 3840, {}), (256, 1280, 3840, dict(split_k=3)), (4096, 320, 2560, dict(geglu=True, pair=True, block_n=256)),
+                              (300, 320, 960, dict(simple=True)), (8192, 320, 960, dict(f32_stream=True))]:
+            x = rnd(m, c)
+            wp = torch.randn(c, c, device=dev) / c ** 0.5
+            res = rnd(m, c) * 2 + 0.7
+            f32s = kw.get("f32_stream", False)
+            t = torch.full((m, c), float("nan"), device=dev, dtype=torch.float32 if f32s else bf)
+            t_sh = torch.full((m, c), float("nan"), device=dev, dtype=bf) if f32s else None
+            rs = torch.zeros(m, 2, device=dev)
+            resid = res.float() if f32s else res
+            p1 = nat.make_igemm_params([x], [c], 1, 1, m, [(0, 1)], pk.to_bf16(pk.tile_pack(pk.pack_linear(wp))), c, t, c,
+                                       residual=resid, res_ld=c, weight_tiled=True, weight_static=True, rowstats_out=rs,
+                                       out2=t_sh)
+            nat.igemm(p1, simple=kw.get("simple", False))
+            trow = t_sh if f32s else t                      # the bf16 rows the consumer multiplies
+            gam, bet = torch.randn(c, device=dev) * 0.5 + 1.0, torch.randn(c, device=dev) * 0.3
+            w = torch.randn(n, c, device=dev) / c ** 0.5
+            b = torch.randn(n, device=dev)
+            wf, cf, colsum = pk.fold_layernorm(w, b, gam, bet)
+            geglu = kw.get("geglu", False)
+            if geglu:
+                wf, cf = pk.interleave_geglu(wf, cf)
+                colsum = wf.to(bf).float().sum(dim=1)
+            n_out = n // 2 if geglu else n
+            out = torch.full((m, n_out), float("nan"), device=dev, dtype=bf)
+            split = kw.get("split_k", 0)
+            ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev) if split > 1 else None
+            cnt = torch.zeros(8192, device=dev, dtype=torch.int32) if split > 1 else None
+            p2 = nat.make_igemm_params([trow], [c], 1, 1, m, [(0, 1)], pk.to_bf16(pk.tile_pack(pk.pack_linear(wf))), n, out, n_out,
+                                       bias=cf.contiguous(), act=nat.ACT_GEGLU if geglu else nat.ACT_NONE, weight_tiled=True,
+                                       weight_static=True, split_k=split, workspace=ws, counters=cnt,
+                                       pair=kw.get("pair", False), block_n=kw.get("block_n", 0), pdl=True,
+                                       ln_rowstats=rs, ln_colsum=colsum.contiguous(), ln_channels=c, ln_eps=1e-5)
+            nat.igemm(p2, simple=kw.get("simple", False))
+            torch.cuda.synchronize()
+            tr = trow.float()
+            ok &= report(f"ln-fold producer row moments m={m} c={c} {kw}", rs, torch.stack([tr.sum(1), (tr * tr).sum(1)], 1), 1e-4)
+            ref = F.layer_norm(tr, (c,), gam, bet, 1e-5) @ w.t() + b
+            if geglu:
+                ref = ref[:, : n // 2] * F.gelu(ref[:, n // 2:])
+            ok &= report(f"ln-fold consumer m={m} c={c} n={n} {kw}", out, ref, 1.2e-2)
     elif group == "xattn":
         # cross-attention: q [nb*ntok, C], kv [nb*T, 2C]; T = 77 (text) / 257 (CLIP patches) / 1 / 128 (queries)
         for (nb, ntok, T, heads, d) in [(2, 4096, 77, 8, 40), (2, 1024, 257, 8, 80), (2, 256, 77, 8, 160),
@@ -559,7 +604,9 @@ def run_group(group):
         import numpy as np
         g = torch.Generator().manual_seed(3)
         nb, s = 3, 64
-        base = torch.randn(nb, 128, 8, 8, generator=g) * 4
+        # a dozen confident classes in 8x8 blobs over a suppressed background: segments above AND below the thresholds
+        base = torch.full((nb, 128, 8, 8), -6.0)
+        base[:, :12] = torch.randn(nb, 12, 8, 8, generator=g) * 6
         logits = F.interpolate(base, size=(s, s), mode="bilinear") + torch.randn(nb, 128, s, s, generator=g) * 0.3
         sizes = [(100, 150), (128, 128), (97, 61)]
         crops = [(0, 0, 2 * s, 2 * s), (0, 0, 2 * s, 100), (8, 4, 96, 120)]
@@ -588,7 +635,9 @@ def run_group(group):
             agree = (got == ref[i][0]).mean()
             kept = sorted(int(c) + 1 for c in keep[i].nonzero().flatten().cpu())
             good = agree >= 0.995 and kept == sorted(ref[i][1])
-            print(f"{'PASS' if good else 'FAIL'} panoptic image {i} ({h}x{w}): id agreement {agree:.5f}, segments {len(kept)} vs {len(ref[i][1])}")
+            good = good and len(kept) >= 2
+            print(f"{'PASS' if good else 'FAIL'} panoptic image {i} ({h}x{w}): id agreement {agree:.5f}, segments {len(kept)} vs {len(ref[i][1])}, "
+                  f"void {float((got == 0).mean()):.3f}")
             ok &= bool(good)
             # integer stage: bit-exact given the kernel's own pred / histograms
             p_np = pred[i, :h * w].view(h, w).cpu().numpy().astype(np.int64)
@@ -606,19 +655,26 @@ def run_group(group):
         from ldmseg.engine import plan as plan_mod
         torch.manual_seed(0)
         vae = GeneralVAEImage().to(dev)
-        for size, nb in ((128, 2), (256, 1)):
-            x = torch.rand(nb, 3, size, size, device=dev) * 2 - 1
+        for size, nb in ((128, 2), (256, 2)):
+            # two different batches alternate, so a launch that read an operand before its producer had written it
+            # would see the OTHER batch's data (an O(1) error), not a harmless copy of the right values
+            xs = [torch.rand(nb, 3, size, size, device=dev) * 2 - 1 for _ in range(2)]
             eng = vae._get_engine()
             pl = eng.plan(nb, size)
             pl.pdl = False
-            ref = eng.encode(x).clone()
+            refs = [eng.encode(x).clone() for x in xs]
+            spread = max(((eng.encode(x) - r).norm() / r.norm()).item() for x, r in zip(xs, refs))
             pl.pdl = True
             worst = 0.0
-            for _ in range(20):
-                out = eng.encode(x)
-                worst = max(worst, ((out - ref).norm() / ref.norm()).item())
-            good = worst < 2e-3
-            print(f"{'PASS' if good else 'FAIL'} VAE encoder {size}px nb={nb}: PDL vs no-PDL worst rel_l2 over 20 runs = {worst:.3e}")
+            for it in range(20):
+                out = eng.encode(xs[it & 1])
+                worst = max(worst, ((out - refs[it & 1]).norm() / refs[it & 1].norm()).item())
+            other = ((refs[0] - refs[1]).norm() / refs[1].norm()).item()
+            # run-to-run spread without PDL (fp32 atomics order -> bf16 rounding flips, amplified by the peaked
+            # single-head softmax of the random-init mid block) is the yardstick
+            good = worst < max(3e-2, 3 * spread) and other > 0.3
+            print(f"{'PASS' if good else 'FAIL'} VAE encoder {size}px nb={nb}: PDL vs no-PDL worst rel_l2 over 20 alternating runs = "
+                  f"{worst:.3e} (no-PDL run-to-run spread {spread:.3e}, distance between the two batches {other:.3e})")
             ok &= good
     torch.cuda.synchronize()
     print(f"GROUP {group}: {'OK' if ok else 'FAILED'}", flush=True)
