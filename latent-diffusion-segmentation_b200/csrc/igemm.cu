@@ -73,6 +73,7 @@ struct alignas(64) IgemmKParams {
   const float* ln_colsum;     // out = rstd_m * (acc - mean_m * colsum[n]) + bias[n]   (bias carries W beta + b)
   float ln_inv_c, ln_eps;
   int w_tiled;        // weights stored as [N/16][K/64][16][64] blocks (2 KB contiguous per block)
+  int coop_reduce;    // split-K: all epilogue warps share the reduction of each owned chunk (see splitk_final_coop)
   int prefetch_b;     // issue the first work item's weight loads before the grid-dependency wait
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
   int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store,
@@ -249,6 +250,20 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fast_silu(v[i]);
       }
+      if (p.rowstats != nullptr && row_ok) {
+        // row moments for a LayerNorm folded into the next GEMM: taken from the f32 values (the bf16 rounding of
+        // the stored row is unbiased: its effect on mean / variance is ~1e-4 relative, far below the output's own
+        // rounding), packed fp32x2 arithmetic
+        float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 x = make_float2(v[2 * i], v[2 * i + 1]);
+          a1 = f2_fma(x, f2_splat(1.f), a1);
+          a2 = f2_fma(x, x, a2);
+        }
+        rs1 += a1.x + a1.y;
+        rs2 += a2.x + a2.y;
+      }
       if (p.out_f32) {
         if (row_ok) {
           float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col0;
@@ -264,14 +279,6 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
             __nv_bfloat16* o2 = p.out2 + static_cast<size_t>(m) * p.out2_ld + col0;
             stg256(o2, o0);
             stg256(o2 + 16, o1);
-            if (p.rowstats != nullptr) {   // of the bf16 shadow: that is what the folding GEMM multiplies
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 a = unpack_bf16x2(o0[i]), b = unpack_bf16x2(o1[i]);
-                rs1 += (a.x + a.y) + (b.x + b.y);
-                rs2 += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
-              }
-            }
           }
         }
       } else {
@@ -286,18 +293,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
           stg256(op, o0);
           stg256(op + 16, o1);
         }
-        if (p.stats != nullptr || p.rowstats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
+        if (p.stats != nullptr) {  // statistics of what the consumer will read (bf16-rounded)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float2 a = unpack_bf16x2(o0[i]), b = unpack_bf16x2(o1[i]);
             v[2 * i] = a.x; v[2 * i + 1] = a.y; v[16 + 2 * i] = b.x; v[17 + 2 * i] = b.y;
-          }
-          if (p.rowstats != nullptr && row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              rs1 += v[i];
-              rs2 = fmaf(v[i], v[i], rs2);
-            }
           }
         }
       }
@@ -331,9 +331,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
         x = __bfloat162float(o);
       }
       if (p.rowstats != nullptr) {
-        const float xb = __bfloat162float(__float2bfloat16(x));
-        rs1 += xb;
-        rs2 = fmaf(xb, xb, rs2);
+        rs1 += x;
+        rs2 = fmaf(x, x, rs2);
       }
       tmp[i] = x;
     }
@@ -366,7 +365,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
 //   FINAL  : sum of the workspace partials -> epilogue -> global, for the chunks dealt to this split
 template <int BN, bool GEGLU, int MODE, int NH>
 __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, float* ws_tile, int split_idx,
-                                              int m_base, int n0, int q, int half, int lane) {
+                                              int m_base, int n0, int q, int half, int lane, float2 ln_rs) {
   constexpr int kChunks = BN / 32;
   constexpr int kTileElems = BM * BN;
   const int m = m_base + lane;
@@ -375,10 +374,9 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
   const int img_stats = MODE == EPI_PARTIAL ? 0 : m_base / p.stats_hw;  // image of the warp's rows (statistics)
   float ln_mu = 0.f, ln_r = 1.f, rs1 = 0.f, rs2 = 0.f;
   if constexpr (MODE != EPI_PARTIAL) {
-    if (p.ln_rowstats != nullptr && m < p.M) {
-      const float2 rs = __ldcg(reinterpret_cast<const float2*>(p.ln_rowstats) + m);
-      ln_mu = rs.x * p.ln_inv_c;
-      ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, rs.y * p.ln_inv_c), 0.f) + p.ln_eps);
+    if (p.ln_rowstats != nullptr) {
+      ln_mu = ln_rs.x * p.ln_inv_c;
+      ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, ln_rs.y * p.ln_inv_c), 0.f) + p.ln_eps);
     }
   }
 #pragma unroll 1
@@ -421,6 +419,85 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
     if (p.rowstats != nullptr && m < p.M) {
       atomicAdd(p.rowstats + 2 * static_cast<size_t>(m), rs1);
       atomicAdd(p.rowstats + 2 * static_cast<size_t>(m) + 1, rs2);
+    }
+  }
+}
+
+// Split-K final pass, cooperative form.  A split CTA owns the (row quadrant, 32-column chunk) units u = split (mod S)
+// of its tile.  In EPI_FINAL above ONE warp sums all S partials of a unit, two splits per trip: with S = 14 that is a
+// chain of seven dependent L2 round trips on a single warp (~5 us of the ~14 us a weight-streaming 8x8 / 16x16
+// convolution takes at batch 1) while the other seven epilogue warps idle.  Here the 8 epilogue warps form teams of
+// T = 8 / (owned units, rounded up to a power of two): member j of a team sums the splits s = j (mod T) of the
+// team's unit, the partial sums meet in shared memory (the operand ring is idle: a split launch gives every CTA
+// exactly one work item), and member 0 finishes the chunk.  One round trip instead of S / 2.
+template <int BN, bool GEGLU>
+__device__ __forceinline__ void splitk_final_coop(const EpiArgs& p, const float* ws_tile, int split_idx, int tile_m0,
+                                                  int n0, int ew, int lane, float* stage) {
+  constexpr int kChunks = BN / 32;
+  constexpr int kUnits = 4 * kChunks;
+  constexpr int kTileElems = BM * BN;
+  const int S = p.split_k;
+  const int n_own = (kUnits - split_idx + S - 1) / S;
+  if (n_own <= 0) return;
+  int T = 8;
+  while (T > 1 && T * n_own > 8) T >>= 1;
+  const int n_teams = 8 / T, team = ew / T, j = ew - team * T;
+  float4* st4 = reinterpret_cast<float4*>(stage);   // [warp][8 float4 groups][32 lanes]
+  for (int k = team; k < n_own; k += n_teams) {
+    const int u = split_idx + k * S;
+    const int q = u / kChunks, ch = u - q * kChunks;
+    const int col0 = n0 + ch * 32;
+    const bool live = col0 < p.N;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    if (live) {
+      const float* src = ws_tile + (static_cast<size_t>(ch) * 4 * BM + q * 32 + lane) * 8;
+#pragma unroll 2
+      for (int s = j; s < S; s += T) {
+        uint32_t t[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ldg256_cg(src + static_cast<size_t>(s) * kTileElems + g * (BM * 8), t[g]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * g + i] += __uint_as_float(t[g][i]);
+      }
+    }
+    if (T > 1) {
+      if (j != 0) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          st4[(ew * 8 + g) * 32 + lane] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(T * 32) : "memory");
+      if (j == 0) {
+        for (int jj = 1; jj < T; ++jj) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 a = st4[((ew + jj) * 8 + g) * 32 + lane];
+            v[4 * g] += a.x; v[4 * g + 1] += a.y; v[4 * g + 2] += a.z; v[4 * g + 3] += a.w;
+          }
+        }
+      }
+      // the team's staging slices are rewritten by its next unit
+      if (k + n_teams < n_own) asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(T * 32) : "memory");
+    }
+    if (j == 0 && live) {
+      const int m = tile_m0 + q * 32 + lane;
+      float ln_mu = 0.f, ln_r = 1.f, rs1 = 0.f, rs2 = 0.f;
+      if (p.ln_rowstats != nullptr && m < p.M) {
+        const float2 rs = __ldcg(reinterpret_cast<const float2*>(p.ln_rowstats) + m);
+        ln_mu = rs.x * p.ln_inv_c;
+        ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, rs.y * p.ln_inv_c), 0.f) + p.ln_eps);
+      }
+      epi_finish<GEGLU>(p, v, m, m / p.HW, (tile_m0 + q * 32) / p.stats_hw, col0, lane, ln_mu, ln_r, rs1, rs2);
+      if constexpr (!GEGLU) {
+        if (p.rowstats != nullptr && m < p.M) {
+          atomicAdd(p.rowstats + 2 * static_cast<size_t>(m), rs1);
+          atomicAdd(p.rowstats + 2 * static_cast<size_t>(m) + 1, rs2);
+        }
+      }
     }
   }
 }
@@ -686,6 +763,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_base = m_tile * BM + q * 32;
       const int n0 = n_tile * BN;
+      // a folded LayerNorm's row moments come from an earlier launch: fetch them while the MMAs are still running
+      float2 ln_rs = make_float2(0.f, 1.f);
+      if (ea.ln_rowstats != nullptr && m_base + lane < ea.M)
+        ln_rs = __ldcg(reinterpret_cast<const float2*>(ea.ln_rowstats) + m_base + lane);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -695,7 +776,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           release_acc(acc);
           continue;
         }
-        epilogue_warp<BN, GEGLU, EPI_DIRECT, NH>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane);
+        epilogue_warp<BN, GEGLU, EPI_DIRECT, NH>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane, ln_rs);
         tc_fence_before();
         release_acc(acc);
       } else {
@@ -703,7 +784,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         // tile have arrived, each split CTA reduces and finishes its share of the tile's chunks.
         float* ws_tile = p.workspace + static_cast<size_t>(tile) * p.split_k * (BM * BN);
         if (!(p.debug & 4))
-          epilogue_warp<BN, GEGLU, EPI_PARTIAL, NH>(ea, t_row, ws_tile, split, m_base, n0, q, half, lane);
+          epilogue_warp<BN, GEGLU, EPI_PARTIAL, NH>(ea, t_row, ws_tile, split, m_base, n0, q, half, lane, ln_rs);
         tc_fence_before();
         release_acc(acc);
         // publish + wait for the peers: the CTA barrier orders every thread's partial stores before
@@ -722,8 +803,15 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           } while (seen < p.split_k);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (!(p.debug & 1))
-          epilogue_warp<BN, GEGLU, EPI_FINAL, NH>(ea, 0, ws_tile, split, m_base, n0, q, half, lane);
+        if (!(p.debug & 1)) {
+          // one work item per CTA (always the case for the planner's split launches): nothing else touches the
+          // operand ring any more, its first 32 KB stage the cooperative reduction
+          if (p.coop_reduce && total_work <= num_units)
+            splitk_final_coop<BN, GEGLU>(ea, ws_tile, split, m_tile * BM, n0, warp - 2, lane,
+                                         reinterpret_cast<float*>(smem_a));
+          else
+            epilogue_warp<BN, GEGLU, EPI_FINAL, NH>(ea, 0, ws_tile, split, m_base, n0, q, half, lane, ln_rs);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
           // the last CTA to finish its share re-arms both counters for the next launch
@@ -1105,6 +1193,14 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   kp.ln_eps = p->ln_eps;
   kp.debug = g_debug;
   kp.w_tiled = p->weight_tiled;
+  {
+    static int coop = -1;  // LDMSEG_SPLITK_COOP=0: one warp per owned chunk sums all partials (A/B timing)
+    if (coop < 0) {
+      const char* e = getenv("LDMSEG_SPLITK_COOP");
+      coop = e ? atoi(e) : 1;
+    }
+    kp.coop_reduce = coop != 0;
+  }
   {
     static int mode = -1;  // LDMSEG_IGEMM_PREFETCH=0 disables (A/B timing)
     if (mode < 0) {

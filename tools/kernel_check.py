@@ -497,7 +497,8 @@ def run_group(group):
             nat.igemm(p2, simple=kw.get("simple", False))
             torch.cuda.synchronize()
             tr = trow.float()
-            ok &= report(f"ln-fold producer row moments m={m} c={c} {kw}", rs, torch.stack([tr.sum(1), (tr * tr).sum(1)], 1), 1e-4)
+            # the moments are taken from the f32 values before the bf16 rounding of the stored row
+            ok &= report(f"ln-fold producer row moments m={m} c={c} {kw}", rs, torch.stack([tr.sum(1), (tr * tr).sum(1)], 1), 1e-3)
             ref = F.layer_norm(tr, (c,), gam, bet, 1e-5) @ w.t() + b
             if geglu:
                 ref = ref[:, : n // 2] * F.gelu(ref[:, n // 2:])
@@ -604,10 +605,17 @@ def run_group(group):
         import numpy as np
         g = torch.Generator().manual_seed(3)
         nb, s = 3, 64
-        # a dozen confident classes in 8x8 blobs over a suppressed background: segments above AND below the thresholds
-        base = torch.full((nb, 128, 8, 8), -6.0)
-        base[:, :12] = torch.randn(nb, 12, 8, 8, generator=g) * 6
-        logits = F.interpolate(base, size=(s, s), mode="bilinear") + torch.randn(nb, 128, s, s, generator=g) * 0.3
+        # one confident winner per 8x8 cell over a suppressed background, so that every rule of the filter fires:
+        # classes 1..9 large segments (kept), class 0 = ignore label (dropped), class 10 a single small cell (dropped by
+        # count_th), class 11 wins two cells but is weakly positive over many more (dropped by overlap_th)
+        win = torch.randint(0, 10, (nb, 8, 8), generator=g)
+        win[:, 0, 0] = 10
+        win[:, 7, 6:8] = 11
+        base = torch.full((nb, 128, 8, 8), -8.0)
+        base.scatter_(1, win[:, None], 8.0)
+        halo = (win != 11) & (torch.rand(nb, 8, 8, generator=g) < 0.6)
+        base[:, 11][halo] = 1.5
+        logits = F.interpolate(base, size=(s, s), mode="nearest") + torch.randn(nb, 128, s, s, generator=g) * 0.3
         sizes = [(100, 150), (128, 128), (97, 61)]
         crops = [(0, 0, 2 * s, 2 * s), (0, 0, 2 * s, 100), (8, 4, 96, 120)]
         cl = logits.permute(0, 2, 3, 1).contiguous().to(dev)
@@ -619,7 +627,7 @@ def run_group(group):
         orig = torch.empty(nb, 128, device=dev, dtype=torch.int32)
         ids = torch.zeros(nb, stride, device=dev, dtype=torch.uint8)
         keep = torch.empty(nb, 128, device=dev, dtype=torch.int32)
-        count_th, overlap_th = 60, 0.5
+        count_th, overlap_th = 300, 0.5
         nat.panoptic_resample(cl, nb, s, 128, 128, geom, max_hw, stride, 0.5, True, pred, area, orig)
         nat.panoptic_filter(pred, nb, geom, max_hw, stride, area, orig, count_th, overlap_th, 0, ids, keep)
         torch.cuda.synchronize()
