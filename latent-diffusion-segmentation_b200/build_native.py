@@ -39,7 +39,14 @@ def _deps():
     return hdrs
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, variant: str = "", extra_flags=()) -> str:
+    """variant: development builds for same-session A/B timing (LDMSEG_LIB=<path> selects one at run time), e.g.
+    `python build_native.py --variant lean -DLDMSEG_EPI_LEAN` -> lib/libldmseg_b200_lean.so."""
+    global BUILD, LIB, FLAGS
+    if variant:
+        BUILD = os.path.join(HERE, f"build_{variant}")
+        LIB = os.path.join(LIBDIR, f"libldmseg_b200_{variant}.so")
+        FLAGS = FLAGS + list(extra_flags)
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     hdrs = _deps()
@@ -80,4 +87,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        build(force=True, variant=sys.argv[i + 1], extra_flags=[a for a in sys.argv[i + 2:] if a.startswith("-D")])
+    else:
+        build(force="--force" in sys.argv)

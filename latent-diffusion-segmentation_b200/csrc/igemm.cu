@@ -109,6 +109,12 @@ struct IgemmCfg {
 //     column sum per lane (31 shuffles per quantity), then one red.global per (lane, quantity).
 // Eight epilogue warps: two per TMEM lane quadrant, taking alternate 32-column chunks of the tile.
 enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2 };
+// -DLDMSEG_EPI_LEAN builds the epilogue without the LayerNorm-fold code (A/B of its cost on launches that do not use it)
+#ifdef LDMSEG_EPI_LEAN
+constexpr bool kEpiLnFold = false;
+#else
+constexpr bool kEpiLnFold = true;
+#endif
 
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // GELU(x) = x/2 (1 + erf(x/sqrt2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
@@ -184,7 +190,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
   const bool row_ok = m < p.M;
   const bool full = (col0 + 32 <= p.N) && p.vec_ok;
   if (full) {
-    if (p.ln_colsum != nullptr) {
+    if (kEpiLnFold && p.ln_colsum != nullptr) {
       const float nmr = -ln_mu * ln_r;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -250,7 +256,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fast_silu(v[i]);
       }
-      if (p.rowstats != nullptr && row_ok) {
+      if (kEpiLnFold && p.rowstats != nullptr && row_ok) {
         // row moments for a LayerNorm folded into the next GEMM: taken from the f32 values (the bf16 rounding of
         // the stored row is unbiased: its effect on mean / variance is ~1e-4 relative, far below the output's own
         // rounding), packed fp32x2 arithmetic
