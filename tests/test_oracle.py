@@ -140,3 +140,59 @@ def test_ddpm_and_inpaint_extensions_are_consistent():
     torch.testing.assert_close(full, rgb)  # fully known region is returned unchanged
     noisy = orc.sample(unet, sched, rgb, 10, seed=1, ddpm=True)
     assert torch.isfinite(noisy).all() and not torch.allclose(noisy, base)
+
+
+def test_panoptic_postprocess_rules():
+    """The oracle transcription of compute_pq's per-image tail (trainers_ldm_cond.py:1261-1313) on structured logits:
+    area rule, ignore label, overlap rule, and agreement of the split (float stage / integer stage) formulation that
+    the CUDA kernels are checked against."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    win = torch.randint(0, 6, (1, 8, 8), generator=g)
+    win[:, 0, 0] = 10                     # one small cell -> below count_th
+    win[:, 7, 6:8] = 11                   # wins two cells ...
+    base = torch.full((1, 128, 8, 8), -8.0)
+    base.scatter_(1, win[:, None], 8.0)
+    halo = (win != 11) & (torch.rand(1, 8, 8, generator=g) < 0.6)
+    base[:, 11][halo] = 1.5               # ... but is weakly positive over many more -> fails overlap_th
+    logits = F.interpolate(base, size=(128, 128), mode="nearest")
+    (seg, ids), = orc.panoptic_postprocess(logits, [(96, 120)], 0.5, 300, 0.5, 0, True)
+    kept = set(ids)
+    assert 1 not in kept                                     # class 0 = ignore label
+    assert 11 not in kept and 12 not in kept                 # count_th / overlap_th
+    assert kept and kept <= {2, 3, 4, 5, 6} and set(np.unique(seg)) == kept | {0}
+    # same result from (pred, area histogram, sigmoid-mask histogram) -> integer stage
+    r = F.interpolate(logits.float(), size=(96, 120), mode="bilinear", align_corners=False)[0]
+    pred = r.argmax(0)
+    pred[F.softmax(r, 0).max(0)[0] < 0.5] = -1
+    pred = pred.numpy()
+    area = np.bincount(pred[pred >= 0].ravel(), minlength=128)
+    orig = (torch.sigmoid(r) >= 0.5).sum((1, 2)).numpy()
+    seg2, ids2 = orc.panoptic_filter(pred, area, orig, None, 300, 0.5, 0)
+    assert ids2 == ids and (seg2 == seg).all()
+
+
+def test_sample_guidance_and_ddpm_seed():
+    """sample(): the doubled batch + guidance combine (trainers_ldm_cond.py:1098-1146) reduces to the plain loop at
+    guidance 1 with identical halves; the DDPM extension draws its noise from seed + 1."""
+    torch.manual_seed(0)
+    u = orc.UNet(**dict(TINY, cross_attention_dim=32))
+    u.modify_encoder(in_channels=8, cond_channels=0)
+    u = u.eval()
+    rgb = torch.randn(1, 4, 8, 8) * 0.5
+    enc = torch.randn(1, 5, 32)
+    enc2 = torch.cat([enc, enc])
+    s = orc.DDIMNoiseScheduler(**SCHED_KW)
+
+    class Fixed(torch.nn.Module):            # the plain loop with the same (conditional) states on a single batch
+        def forward(self, x, t, encoder_hidden_states=None):
+            return u(x, t, encoder_hidden_states=enc)
+    a = orc.sample(u, s, rgb, 3, seed=5, self_condition=False, encoder_hidden_states=enc2, guidance_scale=1.0)
+    b = orc.sample(Fixed(), s, rgb, 3, seed=5, self_condition=False)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    c = orc.sample(u, s, rgb, 3, seed=5, self_condition=False, encoder_hidden_states=enc2, guidance_scale=7.5)
+    assert c.shape == a.shape and torch.isfinite(c).all()
+    d1 = orc.sample(Fixed(), s, rgb, 4, seed=5, self_condition=False, ddpm=True)
+    d2 = orc.sample(Fixed(), s, rgb, 4, seed=6, noise=torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(5)),
+                    self_condition=False, ddpm=True)
+    assert not torch.allclose(d1, d2)            # same initial noise, different ancestral stream
