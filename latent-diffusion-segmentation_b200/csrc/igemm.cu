@@ -396,7 +396,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
       for (int i = 0; i < 32; ++i) v[i] = 0.f;
       const float* src = ws_tile + (static_cast<size_t>(ch) * 4 * BM + row_in_tile) * 8;
 #pragma unroll 2
-      for (int s = 0; s < p.split_k; ++s) {
+      for (int s = 0; s < (m < p.M ? p.split_k : 0); ++s) {
         uint32_t t[4][8];
 #pragma unroll
         for (int g = 0; g < 4; ++g) ldg256_cg(src + static_cast<size_t>(s) * kTileElems + g * (BM * 8), t[g]);
@@ -410,10 +410,13 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
       tmem_ld_32x32(t_row + ch * 32, r);
       tmem_wait_ld();
       if constexpr (MODE == EPI_PARTIAL) {
-        float* dst = ws_tile + static_cast<size_t>(split_idx) * kTileElems +
-                     (static_cast<size_t>(ch) * 4 * BM + row_in_tile) * 8;
+        // rows past M (the 8x8 level fills half a tile at batch 1) are never read back
+        if (m < p.M) {
+          float* dst = ws_tile + static_cast<size_t>(split_idx) * kTileElems +
+                       (static_cast<size_t>(ch) * 4 * BM + row_in_tile) * 8;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) stg256(dst + g * (BM * 8), *reinterpret_cast<uint32_t(*)[8]>(&r[8 * g]));
+          for (int g = 0; g < 4; ++g) stg256(dst + g * (BM * 8), *reinterpret_cast<uint32_t(*)[8]>(&r[8 * g]));
+        }
         continue;
       }
 #pragma unroll
@@ -457,7 +460,7 @@ __device__ __forceinline__ void splitk_final_coop(const EpiArgs& p, const float*
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
-    if (live) {
+    if (live && tile_m0 + q * 32 + lane < p.M) {
       const float* src = ws_tile + (static_cast<size_t>(ch) * 4 * BM + q * 32 + lane) * 8;
 #pragma unroll 2
       for (int s = j; s < S; s += T) {

@@ -204,7 +204,11 @@ static int gn_apply_cs_launch(const void* src0, int c0, const float* chan_stats0
   int ppc = (hw + chunks - 1) / chunks;
   chunks = (hw + ppc - 1) / ppc;
   const size_t smem = 2 * static_cast<size_t>(groups) * sizeof(float);
-  // more loads in flight per thread once a lane has many pixels to walk (batch >= 4: the pass was at 39 % of HBM)
+  // Three shapes of the same kernel.  One trip per thread (batch 1: latency-bound): the loads are hoisted above the
+  // statistics phase (82 registers).  Several trips (batch >= 4: bandwidth-bound): the plain loop at 63 registers keeps
+  // two CTAs per SM (hoisting there cost 160 us per batch-8 forward, profiles/r02_ablate_unet_b8*.log); many trips:
+  // eight loads in flight per thread.
+  const bool one_trip = ppc <= 4 * lanes;
   const bool deep = ppc >= 16 * lanes;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (src_f32)
@@ -213,8 +217,11 @@ static int gn_apply_cs_launch(const void* src0, int c0, const float* chan_stats0
   else if (deep)
     launch_kernel(gn_apply_cs_kernel<8, false, false>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
                   src1, c1, chan_stats1, hw, ppc, groups, gamma, beta, eps, silu, o);
-  else
+  else if (one_trip)
     launch_kernel(gn_apply_cs_kernel<4, false, true>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
+                  src1, c1, chan_stats1, hw, ppc, groups, gamma, beta, eps, silu, o);
+  else
+    launch_kernel(gn_apply_cs_kernel<4, false, false>, dim3(chunks, nb), dim3(threads), smem, st, src0, c0, chan_stats0,
                   src1, c1, chan_stats1, hw, ppc, groups, gamma, beta, eps, silu, o);
   return check_launch("gn_apply_cs_kernel");
 }

@@ -197,8 +197,8 @@ class PlanBase:
         self._chan_stats: Dict[int, torch.Tensor] = {}
         self.rowbias_ld = 0
         self.pdl = USE_PDL
-        arena = self.stats_arena
-        self._op(lambda: arena.zero_(), 1, tag="memset:0:stats_arena")
+        # only the part of the arena the finished plan uses is cleared (known when the first run happens)
+        self._op(lambda: self.stats_arena[: max(self._arena_used, 1)].zero_(), 1, tag="memset:0:stats_arena")
 
     def _buf(self, rows, c, dtype=torch.bfloat16):
         t = torch.empty(rows, c, device=self.device, dtype=dtype)
