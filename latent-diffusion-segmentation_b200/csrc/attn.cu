@@ -1,5 +1,6 @@
 // Self-attention forward (non-causal) on tcgen05: S = Q K^T into TMEM, online softmax in
-// registers (exp2, fp32 statistics), P (bf16) through shared memory, O += P V accumulated in TMEM.
+// registers (exp2, fp32 statistics), P (bf16) back into TMEM as the A operand of O += P V (tcgen05.mma with A
+// from tensor memory), O accumulated in TMEM.  (PT = false keeps the older form with P staged in shared memory.)
 //
 // Replaces F.scaled_dot_product_attention inside diffusers' AttnProcessor2_0 for the 16
 // Transformer2DModel blocks reached from /root/reference/ldmseg/models/unet.py:361-425
@@ -15,9 +16,16 @@
 // with its own softmax warpgroup; while one warpgroup exponentiates S_j the tensor core computes the
 // other tile's S and P.V (ping-pong), and K/V tiles are loaded once for both.
 //
-// CTA = 320 threads:  warp 0 TMA producer | warp 1 MMA issuer + TMEM allocator |
-//                     warps 2..5 softmax/correction of query tile 0 | warps 6..9 of query tile 1
-// TMEM: S0 at [0,BKV), S1 at [BKV,2BKV), O0 at [2BKV, 2BKV+dk), O1 at [2BKV+dk, 2BKV+2dk)  (<= 448 columns).
+// CTA = 384 threads:  warps 0..3 softmax/correction of query tile 0 | warps 4..7 of query tile 1 |
+//                     warps 8 / 9 MMA issuer of query tile 0 / 1 (8 allocates TMEM) | warp 10 TMA producer | warp 11 idle
+// TMEM: S0 at [0,BKV), S1 at [BKV,2BKV), O0 at [2BKV, 2BKV+dk), O1 at [2BKV+dk, 2BKV+2dk), then P0, P1 (BKV/2
+// columns each: two bf16 per 32-bit cell, K-contiguous -- the layout tcgen05.mma expects of a K-major A operand in
+// tensor memory)  (<= 512 columns: 480 / 352 / 512 at d = 40 / 80 / 160).
+//
+// Why P lives in TMEM: with both operands in shared memory the tensor core fetches A (128 x 16 bf16 = 4 KB) and B for
+// every K = 16 instruction at ~74 B/clk, so P.V (N = d <= 64, eight instructions per 128 keys) cost ~75 cycles per
+// instruction against a 24-32 cycle math floor, and the P tile crossed shared memory twice (st.shared + operand
+// fetch).  The MMA side, not the exponentials, was what the softmax warps waited for (ncu: tensor 24 %, MUFU 50 %).
 #include "common.h"
 #include <cstdlib>
 #include <cstring>
@@ -26,7 +34,18 @@
 
 namespace ldm {
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 384;
+// Warp roles: two softmax warpgroups (query tile 0 / 1), and a control warpgroup with ONE MMA-issuing warp PER query
+// tile, the TMA producer and an idle warp.  Per tile the order of the tensor-core work is fixed -- S(j+1) becomes
+// issuable (S(j) copied to registers) before P(j) is ready -- so each issuer runs a plain blocking sequence of
+// mbarrier waits.  A single issuer serving both tiles had to poll four barriers in an event loop; a polling round
+// took ~700 cycles and with every stage of the pipeline removed but the hand-shakes the kernel still ran at half
+// its full time (tools/attn_timing.py, ablation builds).
+// Three warpgroups also let the register file be re-split (setmaxnreg works on aligned groups of four warps): the
+// control warpgroup gives up all but 40 registers per thread, the softmax warpgroups grow from 168 to 232 -- a thread
+// holds a whole 128-column score row plus the packed P.
+constexpr int kSoftmaxWarp0 = 0, kCtrlWarp0 = 8, kMmaWarp0 = 8, kTmaWarp = 10;
+constexpr int kCtrlRegs = 40, kSoftmaxRegs = 232;
 
 template <int D>
 struct AttnCfg {
@@ -42,6 +61,8 @@ struct AttnCfg {
   static constexpr int kSmemBytes = 2 * kQBytes + kKVStages * 2 * kKBytes + 2 * kPBytes + 24 * 8 + 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kOCol = 2 * BKV;   // S0 at [0,BKV), S1 at [BKV,2BKV), then O0, O1 (dk columns each)
+  static constexpr int kPCol = kOCol + 2 * kDK;   // P0, P1: BKV/2 columns each (bf16 pairs)
+  static_assert(kPCol + BKV <= 512, "TMEM budget");
 };
 
 struct alignas(64) AttnKParams {
@@ -53,6 +74,8 @@ struct alignas(64) AttnKParams {
   int k_which, v_which;  // index of K / V along the "which" dimension of map_kv (1, 2 in a fused QKV; 0, 1 in a KV tensor)
   float scale_log2;  // (1/sqrt(d)) * log2(e)
 };
+// -DLDMSEG_ATTN_ABLATE=<mask> builds (timing experiments, results are garbage): bit0 no exponentials, bit1 S row read
+// from TMEM only once, bit2 no P.V products, bit3 no S products, bit4 no P store, bit5 no row maximum, bit6 no K/V loads after the first ring fill
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -113,8 +136,23 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 }
 constexpr float kRescaleLog2 = 8.f;
 
+// -DLDMSEG_ATTN_TIMING builds: CTA 0 accumulates clock() deltas per phase (softmax warp 2 -> [0..7], warp 6 ->
+// [8..15], MMA thread -> [16..23]); read back with ldmseg_attn_timing_read.
+#ifdef LDMSEG_ATTN_TIMING
+__device__ unsigned int g_attn_timing[32];
+#define ATT_TICK(acc_i)                      \
+  do {                                       \
+    const unsigned int now_ = clock();       \
+    tacc[acc_i] += now_ - tlast;             \
+    tlast = now_;                            \
+  } while (0)
+#else
+#define ATT_TICK(acc_i) do {} while (0)
+#endif
+
 // PM: share of the exponentials evaluated on the FMA pipe (0 = none, 1 = half, 2 = a quarter)
-template <int D, int PM>
+// PT: P goes to tensor memory (A operand from TMEM) instead of shared memory
+template <int D, int PM, bool PT>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<D>;
   constexpr int BKV = Cfg::BKV;
@@ -141,6 +179,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef LDMSEG_ATTN_ABLATE
+  constexpr int dbg = LDMSEG_ATTN_ABLATE;   // compile-time mask: a run-time one costs the d = 40 kernel 320 B of spills
+#else
+  constexpr int dbg = 0;
+#endif
 
   const int q_blocks = (p.ntok + 255) / 256;
   const int qb = blockIdx.x % q_blocks;
@@ -149,13 +192,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   const int q0 = qb * 256;
   const int T = (p.ntok_kv + BKV - 1) / BKV;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&p.map_q);
     tma_prefetch_desc(&p.map_kv);
     mbar_init(q_full, 1);
     for (int i = 0; i < KS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);   // both tiles' issuers release a stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -165,7 +208,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp0) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -178,7 +221,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   pdl_trigger();
   pdl_wait();  // the prologue above overlapped the previous kernel; inputs are read from here on
 
-  if (warp == 0) {
+  if (warp >= kCtrlWarp0 && warp < kCtrlWarp0 + 4) setmaxnreg_dec<kCtrlRegs>();
+  if (warp == kTmaWarp) {
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * Cfg::kQBytes);
       for (int t = 0; t < 2; ++t)
@@ -189,6 +233,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         const int st = j % KS;
         const uint32_t n = static_cast<uint32_t>(j / KS);
         mbar_wait(&kv_empty[st], (n & 1) ^ 1);
+        if ((dbg & 64) && j >= KS) {   // ablation: stage contents stay stale
+          mbar_arrive(&kv_full[st]);
+          continue;
+        }
         mbar_expect_tx(&kv_full[st], 2 * Cfg::kKBytes);
         for (int pn = 0; pn < kPanels; ++pn) {
           tma_load_5d(sm_k + st * Cfg::kKBytes + pn * BKV * 128, &p.map_kv, &kv_full[st], pn * 64,
@@ -199,13 +247,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp0 || warp == kMmaWarp0 + 1) {
     if (elect_one()) {
+      const int t = warp - kMmaWarp0;   // the query tile this issuer serves
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, kDK, 0, 1);
-      auto issue_s = [&](int j, int t) {  // S_t = Q_t K_j^T
+      auto issue_s = [&](int j) {  // S_t = Q_t K_j^T
         const int st = j % KS;
         const uint32_t d_tmem = tmem_base + t * BKV;
+        if ((dbg & 8) && j > 0) return;
 #pragma unroll
         for (int ks = 0; ks < kDK / 16; ++ks) {
           const int pn = ks >> 2, kk = ks & 3;
@@ -216,61 +266,67 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
           umma_bf16(d_tmem, a, bd, idesc_s, ks > 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int j, int t) {  // O_t += P_t V_j
+      auto issue_pv = [&](int j) {  // O_t += P_t V_j
         const int st = j % KS;
         const uint32_t o_tmem = tmem_base + Cfg::kOCol + t * kDK;
+        if ((dbg & 4) && j > 0) return;
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
           const int pn = ks >> 2, kk = ks & 3;
-          const uint64_t a =
-              make_smem_desc_sw128(smem_u32(sm_p + t * Cfg::kPBytes + pn * 128 * 128), 16, 1024) + 2 * kk;
           // V tile: rows = kv (128 B each), MN(d)-major; 16 kv rows per k-step = 2048 B
           const uint64_t bd =
               make_smem_desc_sw128(smem_u32(sm_v + st * Cfg::kKBytes + ks * 2048), BKV * 128, 1024);
-          umma_bf16(o_tmem, a, bd, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          if constexpr (PT) {
+            // A = P_t from tensor memory: 16 keys = 8 columns of bf16 pairs per k-step
+            umma_bf16_ts(o_tmem, tmem_base + Cfg::kPCol + t * (BKV / 2) + ks * 8, bd, idesc_pv,
+                         (j > 0 || ks > 0) ? 1u : 0u);
+          } else {
+            const uint64_t a =
+                make_smem_desc_sw128(smem_u32(sm_p + t * Cfg::kPBytes + pn * 128 * 128), 16, 1024) + 2 * kk;
+            umma_bf16(o_tmem, a, bd, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          }
         }
       };
+#ifdef LDMSEG_ATTN_TIMING
+      unsigned int tacc[4] = {0, 0, 0, 0}, tlast = clock();
+#endif
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      umma_commit(&s_full[0]);
-      issue_s(0, 1);
-      umma_commit(&s_full[1]);
-      // Event loop: the two query tiles advance independently.  Issuing in a fixed order (wait S-free of tile 0,
-      // wait P of tile 0, then tile 1, ...) made each softmax warpgroup wait for the other one's exponentials
-      // before its next S product was even issued.
-      int js[2] = {1, 1};   // next S product to issue per query tile (S_0 is already in flight)
-      int jp[2] = {0, 0};   // next P.V product to issue per query tile
-      while (jp[0] < T || jp[1] < T) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          // S_t(j): needs the warpgroup to have copied S_t(j-1) to registers, and K tile j in shared memory
-          if (js[t] < T && mbar_test_wait(&s_free[t], static_cast<uint32_t>(js[t] - 1) & 1) &&
-              mbar_test_wait(&kv_full[js[t] % KS], static_cast<uint32_t>(js[t] / KS) & 1)) {
-            tc_fence_after();
-            issue_s(js[t], t);
-            umma_commit(&s_full[t]);
-            ++js[t];
-          }
-          // O_t += P_t(j) V_j
-          if (jp[t] < T && mbar_test_wait(&p_full[t], static_cast<uint32_t>(jp[t]) & 1)) {
-            tc_fence_after();
-            const int j = jp[t];
-            issue_pv(j, t);
-            umma_commit(&pv_done[t]);
-            ++jp[t];
-            // K/V stage j&1 can be refilled once both P.V products of tile j are queued (the S products that
-            // read its K half were issued before the P tiles they lead to)
-            if (jp[t ^ 1] > j) umma_commit(&kv_empty[j % KS]);
-          }
+      issue_s(0);
+      umma_commit(&s_full[t]);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          // S_t(j+1): needs the warpgroup to have copied S_t(j) to registers, and K tile j+1 in shared memory
+          mbar_wait(&s_free[t], static_cast<uint32_t>(j) & 1);
+          mbar_wait(&kv_full[(j + 1) % KS], static_cast<uint32_t>((j + 1) / KS) & 1);
+          tc_fence_after();
+          ATT_TICK(0);   // waiting
+          issue_s(j + 1);
+          umma_commit(&s_full[t]);
+          ATT_TICK(1);
         }
+        // O_t += P_t(j) V_j
+        mbar_wait(&p_full[t], static_cast<uint32_t>(j) & 1);
+        tc_fence_after();
+        ATT_TICK(0);
+        issue_pv(j);
+        umma_commit(&pv_done[t]);
+        // K/V stage j can be refilled once both tiles' products that read it have completed (this issuer's S_t(j)
+        // and P_t(j).V_j precede the commit; the barrier counts both issuers)
+        umma_commit(&kv_empty[j % KS]);
+        ATT_TICK(2);
       }
+#ifdef LDMSEG_ATTN_TIMING
+      if (blockIdx.x == 0)
+        for (int i = 0; i < 3; ++i) g_attn_timing[16 + 4 * t + i] = tacc[i];
+#endif
     }
     __syncwarp();
-  } else {
+  } else if (warp >= kSoftmaxWarp0 && warp < kSoftmaxWarp0 + 8) {
     // ---------------------------------------------------------------- softmax / correction
-    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    setmaxnreg_inc<kSoftmaxRegs>();
+    const int t = (warp - kSoftmaxWarp0) >> 2;  // query tile of this warpgroup
     const int q = warp & 3;         // TMEM lane quadrant
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -279,16 +335,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     const uint32_t my_p_u32 = smem_u32(sm_p + t * Cfg::kPBytes);
     const float scale = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
+#ifdef LDMSEG_ATTN_TIMING
+    unsigned int tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock();
+#endif
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[t], static_cast<uint32_t>(j) & 1);
       tc_fence_after();
+      ATT_TICK(0);   // wait for S
       // the whole score row goes to registers in one pass; S_t in TMEM is then free for the next product
       uint32_t sr[BKV];
+      if (!(dbg & 2) || j == 0) {
 #pragma unroll
-      for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(s_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
-      tmem_wait_ld();
+        for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(s_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
+        tmem_wait_ld();
+      }
       tc_fence_before();
       mbar_arrive(&s_free[t]);
+      ATT_TICK(1);   // S row -> registers
       const int kv_valid = p.ntok_kv - j * BKV;  // columns < kv_valid are real tokens
       if (kv_valid < BKV) {
 #pragma unroll
@@ -304,7 +367,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         mx2 = max3f(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
         mx3 = max3f(mx3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;
+      if (dbg & 32) mx = __uint_as_float(sr[0]) * scale;
       // lazy rescaling: the running maximum only moves when the new one exceeds it by more than 2^8, so P
       // stays <= 256 (exact in bf16's range, fp32 accumulation) and O is corrected a handful of times per row
       float alpha = 1.f;
@@ -313,6 +377,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         m_run = mx;
       }
       const float negm = -m_run;
+      ATT_TICK(2);   // row maximum
       // p = exp2(s*scale - m): packed FFMA2, one MUFU each, packed FADD2 row sums, bf16 pairs
       float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
       uint32_t pk[BKV / 2];
@@ -320,11 +385,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       for (int i = 0; i < BKV; i += 4) {
         float2 a = fma2(make_float2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), scale, negm);
         float2 b = fma2(make_float2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), scale, negm);
-        a.x = ex2_approx(a.x); a.y = ex2_approx(a.y);
-        if (PM == 1 || (PM == 2 && ((i >> 2) & 1))) {
-          b = exp2_poly2(b);
-        } else {
-          b.x = ex2_approx(b.x); b.y = ex2_approx(b.y);
+        if (!(dbg & 1)) {
+          a.x = ex2_approx(a.x); a.y = ex2_approx(a.y);
+          if (PM == 1 || (PM == 2 && ((i >> 2) & 1))) {
+            b = exp2_poly2(b);
+          } else {
+            b.x = ex2_approx(b.x); b.y = ex2_approx(b.y);
+          }
         }
         rs0 = add2(rs0, a);
         rs1 = add2(rs1, b);
@@ -332,17 +399,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         pk[i / 2 + 1] = pack_bf16x2(b.x, b.y);
       }
       l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
+      ATT_TICK(4);   // exponentials, row sums, packing
       // the P buffer and O are free once P.V of the previous tile has completed
       if (j > 0) {
         mbar_wait(&pv_done[t], static_cast<uint32_t>(j - 1) & 1);
         tc_fence_after();
       }
+      ATT_TICK(5);   // wait for P.V
+      if (dbg & 16) {
+      } else if constexpr (PT) {
+        // thread = query row = TMEM lane: its BKV/2 packed pairs go to consecutive columns of P_t
+        const uint32_t p_addr = tmem_base + lane_off + Cfg::kPCol + t * (BKV / 2);
 #pragma unroll
-      for (int c8 = 0; c8 < BKV / 8; ++c8) {
-        const uint32_t prow = my_p_u32 + (c8 >> 3) * (128 * 128) + row * 128;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((c8 & 7) ^ (row & 7)) << 4)),
-                     "r"(pk[4 * c8]), "r"(pk[4 * c8 + 1]), "r"(pk[4 * c8 + 2]), "r"(pk[4 * c8 + 3])
-                     : "memory");
+        for (int c = 0; c < BKV / 2; c += 32) tmem_st_32x32(p_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&pk[c]));
+      } else {
+#pragma unroll
+        for (int c8 = 0; c8 < BKV / 8; ++c8) {
+          const uint32_t prow = my_p_u32 + (c8 >> 3) * (128 * 128) + row * 128;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (((c8 & 7) ^ (row & 7)) << 4)),
+                       "r"(pk[4 * c8]), "r"(pk[4 * c8 + 1]), "r"(pk[4 * c8 + 2]), "r"(pk[4 * c8 + 3])
+                       : "memory");
+        }
       }
       // correction: O *= alpha (skipped warp-uniformly when no row of this warp moved its max)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
@@ -356,12 +433,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
           tmem_st_32x8(o_addr + c, *reinterpret_cast<uint32_t(*)[8]>(&r[0]));
           tmem_st_32x8(o_addr + c + 8, *reinterpret_cast<uint32_t(*)[8]>(&r[8]));
         }
-        tmem_wait_st();
       }
-      fence_proxy_async_smem();
+      if constexpr (PT) tmem_wait_st();        // P (and the corrected O) are in tensor memory before the MMA reads them
+      else {
+        tmem_wait_st();
+        fence_proxy_async_smem();
+      }
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      ATT_TICK(6);   // P store (+ correction)
     }
+#ifdef LDMSEG_ATTN_TIMING
+    if (blockIdx.x == 0 && lane == 0 && q == 0)
+      for (int i = 0; i < 8; ++i) g_attn_timing[t * 8 + i] = tacc[i];
+#endif
     // ---------------------------------------------------------------- final normalisation
     mbar_wait(&pv_done[t], static_cast<uint32_t>(T - 1) & 1);
     tc_fence_after();
@@ -386,7 +471,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -454,7 +539,7 @@ __global__ void attn_simple_kernel(const __nv_bfloat16* __restrict__ qkv, int nb
 
 // q_src: bf16 [nb*ntok, q_which_n * heads * D] (column block 0 = Q); kv_src: bf16 [nb*ntok_kv, kv_which_n * heads * D]
 // with K / V in column blocks k_which / v_which.  Self-attention: q_src = kv_src = the fused QKV, (3, 1, 2).
-template <int D, int PM>
+template <int D, int PM, bool PT>
 static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which,
                           int v_which, int nb, int ntok, int ntok_kv, int heads, void* out, cudaStream_t st) {
   using Cfg = AttnCfg<D>;
@@ -481,12 +566,12 @@ static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, 
   kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = nb * heads * ((ntok + 255) / 256);
-  launch_kernel(attn_kernel<D, PM>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
+  launch_kernel(attn_kernel<D, PM, PT>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
   return check_launch("attn_kernel");
 }
 
@@ -498,11 +583,26 @@ static int launch_attn(const void* q_src, int q_which_n, const void* kv_src, int
     const char* e = getenv("LDMSEG_ATTN_POLY");
     pm = e ? atoi(e) : 2;
   }
-  switch (pm) {
-    case 0: return launch_attn_pm<D, 0>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
-    case 1: return launch_attn_pm<D, 1>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
-    default: return launch_attn_pm<D, 2>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st);
+  static int pt = -1;   // LDMSEG_ATTN_PTMEM=0: P through shared memory (the older form; A/B timing)
+  if (pt < 0) {
+    const char* e = getenv("LDMSEG_ATTN_PTMEM");
+    pt = e ? atoi(e) : 1;
   }
+#define LDM_ATTN_CASE(PMV, PTV) \
+  return launch_attn_pm<D, PMV, PTV>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st)
+  if (pt) {
+    switch (pm) {
+      case 0: LDM_ATTN_CASE(0, true);
+      case 1: LDM_ATTN_CASE(1, true);
+      default: LDM_ATTN_CASE(2, true);
+    }
+  }
+  switch (pm) {
+    case 0: LDM_ATTN_CASE(0, false);
+    case 1: LDM_ATTN_CASE(1, false);
+    default: LDM_ATTN_CASE(2, false);
+  }
+#undef LDM_ATTN_CASE
 }
 
 static int attn_dispatch(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which,
@@ -518,6 +618,12 @@ static int attn_dispatch(const void* q_src, int q_which_n, const void* kv_src, i
 }  // namespace ldm
 
 using namespace ldm;
+
+#ifdef LDMSEG_ATTN_TIMING
+extern "C" int ldmseg_attn_timing_read(unsigned int* dst32) {
+  return static_cast<int>(cudaMemcpyFromSymbol(dst32, g_attn_timing, sizeof(unsigned int) * 32));
+}
+#endif
 
 extern "C" int ldmseg_attention(const void* qkv, int nb, int ntok, int heads, int d, void* out,
                                 void* stream) {
