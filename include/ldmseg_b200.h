@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LDMSEG_ABI_VERSION 2
+#define LDMSEG_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ldmseg_version(void);
@@ -122,6 +122,12 @@ typedef struct ldmseg_igemm_params {
   const float* ln_colsum;            /* consumer: f32 [n] */
   int ln_channels;                   /* consumer: row width C of the LayerNorm (mean = sum / C) */
   float ln_eps;
+  /* ---- ABI version 3 ---- */
+  int stream_k;                      /* 1: stream-K tail.  The tiles past the last whole wave of the persistent grid are
+                                        cut along K into one contiguous piece per CTA; pieces that end inside a tile
+                                        go through `workspace` / `tile_counters` (same buffers as split_k, which must
+                                        be 0/1) and the CTA holding a tile's last k-block finishes it.  Ignored (whole
+                                        tiles) when the last wave is full, for GEGLU and for block_n 64 */
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);

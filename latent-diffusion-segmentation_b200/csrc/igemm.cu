@@ -75,6 +75,10 @@ struct alignas(64) IgemmKParams {
   int w_tiled;        // weights stored as [N/16][K/64][16][64] blocks (2 KB contiguous per block)
   int coop_reduce;    // split-K: all epilogue warps share the reduction of each owned chunk (see splitk_final_coop)
   int prefetch_b;     // issue the first work item's weight loads before the grid-dependency wait
+  int tail;            // stream-K tail (see TailSeg): tiles [0, tail_full_tiles) run whole, in waves of the grid; the
+  int tail_full_tiles; // tail_tiles after them are cut along K into one contiguous piece per CTA
+  int tail_tiles;
+  int tail_slots;      // workspace slots (partial tiles) per tail tile
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
   int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store,
                       // bit3 / bit4 leave the A / B loads out after a work item's first k-block, bit5 drop the epilogue
@@ -108,7 +112,7 @@ struct IgemmCfg {
 //   * fused GroupNorm statistics: a 5-step exchange butterfly turns 32 per-row values x 32 lanes into one
 //     column sum per lane (31 shuffles per quantity), then one red.global per (lane, quantity).
 // Eight epilogue warps: two per TMEM lane quadrant, taking alternate 32-column chunks of the tile.
-enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2 };
+enum { EPI_DIRECT = 0, EPI_PARTIAL = 1, EPI_FINAL = 2, EPI_DIRECT_ADD = 3 };
 // -DLDMSEG_EPI_LEAN builds the epilogue without the LayerNorm-fold code (A/B of its cost on launches that do not use it)
 #ifdef LDMSEG_EPI_LEAN
 constexpr bool kEpiLnFold = false;
@@ -369,6 +373,8 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
 // lane quadrant)
 //   DIRECT : TMEM -> epilogue -> global            PARTIAL: TMEM -> split-K workspace
 //   FINAL  : sum of the workspace partials -> epilogue -> global, for the chunks dealt to this split
+//   DIRECT_ADD: TMEM + the first `split_idx` workspace partials -> epilogue -> global (stream-K tail: the CTA that
+//               holds a tile's last k-blocks finishes it)
 template <int BN, bool GEGLU, int MODE, int NH>
 __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, float* ws_tile, int split_idx,
                                               int m_base, int n0, int q, int half, int lane, float2 ln_rs) {
@@ -409,6 +415,21 @@ __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, 
       uint32_t r[32];
       tmem_ld_32x32(t_row + ch * 32, r);
       tmem_wait_ld();
+      if constexpr (MODE == EPI_DIRECT_ADD) {
+        if (m < p.M) {
+          const float* src = ws_tile + (static_cast<size_t>(ch) * 4 * BM + row_in_tile) * 8;
+#pragma unroll 1
+          for (int s = 0; s < split_idx; ++s) {
+            uint32_t t[4][8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ldg256_cg(src + static_cast<size_t>(s) * kTileElems + g * (BM * 8), t[g]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[8 * g + i] = __float_as_uint(__uint_as_float(r[8 * g + i]) + __uint_as_float(t[g][i]));
+          }
+        }
+      }
       if constexpr (MODE == EPI_PARTIAL) {
         // rows past M (the 8x8 level fills half a tile at batch 1) are never read back
         if (m < p.M) {
@@ -511,9 +532,55 @@ __device__ __forceinline__ void splitk_final_coop(const EpiArgs& p, const float*
   }
 }
 
-template <int BN, bool GEGLU, bool SPLIT, bool PAIR>
+// ---- stream-K tail ---------------------------------------------------------------------------
+// A persistent grid of G units (CTAs, or CTA pairs) runs T tiles in ceil(T / G) waves; the last wave is only
+// (T mod G) / G full (N = 320 at a 64x64 latent, batch 8: 512 tiles on 148 SMs = 3.46 waves paid as 4; 256 tiles as 2).
+// With `tail` set, only the floor(T / G) whole waves run as whole tiles.  The R = T mod G tiles left are laid end to
+// end as U = R * num_kb k-block steps and cut into G equal contiguous pieces, one per unit (U >= G, so no piece is
+// empty, and R < G, so a piece is shorter than a tile and touches at most two).  A piece that ends inside a tile is a
+// PARTIAL: its accumulator goes to a workspace slot and a per-tile counter is bumped.  The unit whose piece holds a
+// tile's LAST k-block finishes the tile: it waits for the counter, adds the partials to its own accumulator and runs
+// the normal epilogue.  A unit whose piece spans two tiles does the head of the second tile (a partial somebody else
+// waits for) BEFORE the end of the first (which it finishes itself), so no unit waits before it has published
+// everything others need from it: no chains of waits, no deadlock as long as the grid is co-resident (1 CTA per SM,
+// grid <= #SMs -- the same premise as split-K).
+struct TailSeg {
+  int tile;        // unit-tile index (a pair tile for PAIR)
+  int kb0, kb1;    // k-block range
+  int slot;        // workspace slot of a partial, or the number of partials to add for the finishing piece
+  int finish;
+};
+// the unit whose piece holds step x:  the largest g with floor(g * U / G) <= x
+__device__ __forceinline__ int tail_owner(long long x, int G, long long U) {
+  return static_cast<int>(((x + 1) * G - 1) / U);
+}
+__device__ __forceinline__ int tail_plan(int tail_full_tiles, int tail_tiles, int num_kb, int unit, int G,
+                                         TailSeg& s0, TailSeg& s1) {
+  const long long U = static_cast<long long>(tail_tiles) * num_kb;
+  const long long u0 = unit * U / G, u1 = (unit + 1) * U / G;
+  if (u1 <= u0) return 0;
+  const int t0 = static_cast<int>(u0 / num_kb), t1 = static_cast<int>((u1 - 1) / num_kb);
+  auto fill = [&](TailSeg& s, int t, long long a, long long b) {
+    const long long base = static_cast<long long>(t) * num_kb;
+    s.tile = tail_full_tiles + t;
+    s.kb0 = static_cast<int>(a - base);
+    s.kb1 = static_cast<int>(b - base);
+    s.finish = s.kb1 == num_kb;
+    s.slot = unit - tail_owner(base, G, U);   // pieces of this tile before mine = my slot = what the finisher adds
+  };
+  if (t0 == t1) {
+    fill(s0, t0, u0, u1);
+    return 1;
+  }
+  fill(s0, t1, static_cast<long long>(t1) * num_kb, u1);   // head of the next tile first
+  fill(s1, t0, u0, static_cast<long long>(t1) * num_kb);   // then the end of this one
+  return 2;
+}
+
+template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false>
 __global__ void __launch_bounds__(igemm_threads(GEGLU, SPLIT), 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
+  static_assert(!(TAIL && (SPLIT || GEGLU)), "the stream-K tail replaces split-K; it is not built for GEGLU");
   using Cfg = IgemmCfg<BN, PAIR>;
   constexpr int kEpiWarps = igemm_epi_warps(GEGLU, SPLIT);
   constexpr int kEpiThreads = kEpiWarps * 32;
@@ -576,6 +643,43 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   // its loads are zero-filled by TMA and its rows are masked in the epilogue)
   const int num_tiles = (PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
   const int total_work = num_tiles * p.split_k;
+  // The it-th work item of this unit: (unit tile, k-split index, k-block range).  TAIL: whole tiles first, then the
+  // unit's one or two pieces of the tail (split = 0 whole tile, 1 partial, 2 finishing piece; slot as in TailSeg).
+  TailSeg ts0 = {0, 0, 0, 0, 0}, ts1 = {0, 0, 0, 0, 0};
+  int tail_n = 0, n_whole = 0;
+  if constexpr (TAIL) {
+    n_whole = p.tail_full_tiles / num_units;
+    tail_n = tail_plan(p.tail_full_tiles, p.tail_tiles, p.num_kb, unit, num_units, ts0, ts1);
+  }
+  auto get_item = [&](int it, int& tile, int& split, int& kb_begin, int& kb_end, int& slot) -> bool {
+    if constexpr (TAIL) {
+      if (it >= n_whole + tail_n) return false;
+      if (it < n_whole) {
+        tile = unit + it * num_units;
+        split = 0;
+        kb_begin = 0;
+        kb_end = p.num_kb;
+        slot = 0;
+      } else {
+        const bool first = it == n_whole;
+        tile = first ? ts0.tile : ts1.tile;
+        kb_begin = first ? ts0.kb0 : ts1.kb0;
+        kb_end = first ? ts0.kb1 : ts1.kb1;
+        slot = first ? ts0.slot : ts1.slot;
+        split = (first ? ts0.finish : ts1.finish) ? 2 : 1;
+      }
+      return true;
+    } else {
+      const int wi = unit + it * num_units;
+      if (wi >= total_work) return false;
+      tile = wi / p.split_k;
+      split = wi - tile * p.split_k;
+      kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
+      kb_end = static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
+      slot = 0;
+      return true;
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -603,12 +707,9 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       // (-3 % on the batch-1 forward).  Also pulling the rest of the weight slice into L2 from here was measured
       // and dropped: at batch 8 many M-tiles share a slice and the redundant prefetches cost more than they hide.
       int prefetched = 0;
-      if (p.prefetch_b && unit < total_work) {
-        const int tile = unit / p.split_k;
-        const int split = unit - tile * p.split_k;
+      int tile, split, kb_begin, kb_end, slot;
+      if (p.prefetch_b && get_item(0, tile, split, kb_begin, kb_end, slot)) {
         const int n_tile = tile % p.num_n_tiles;
-        const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
-        const int kb_end = static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
         prefetched = min(kStages, kb_end - kb_begin);
         for (int i = 0; i < prefetched; ++i) {
           arm(i);
@@ -618,9 +719,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       pdl_wait();  // activations (and everything else the predecessor wrote) from here on
       int stage = 0;
       uint32_t phase = 0;
-      for (int wi = unit; wi < total_work; wi += num_units) {
-        const int tile = wi / p.split_k;
-        const int split = wi - tile * p.split_k;
+      for (int it = 0; get_item(it, tile, split, kb_begin, kb_end, slot); ++it) {
         const int m_unit = tile / p.num_n_tiles;
         const int n_tile = tile - m_unit * p.num_n_tiles;
         const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
@@ -628,9 +727,6 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         const int x0 = (m0 % p.W) * p.a_stride;
         const int y0 = ((m0 / p.W) % p.H) * p.a_stride;
         const int b0 = m0 / p.HW;
-        const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
-        const int kb_end =
-            static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
         // decode kb_begin -> (segment, tap, channel block)
         int seg = 0, rem = kb_begin;
         while (seg < p.nseg - 1 && rem >= p.seg_taps[seg] * p.seg_cblocks[seg]) {
@@ -700,13 +796,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       const uint32_t a_lo = (smem_u32(smem_a) & 0x3FFFF) >> 4, b_lo = (smem_u32(smem_b) & 0x3FFFF) >> 4;
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int wi = unit; wi < total_work; wi += num_units, ++it) {
-        const int tile = wi / p.split_k;
-        const int split = wi - tile * p.split_k;
-        const int kb_begin = static_cast<int>(static_cast<long long>(split) * p.num_kb / p.split_k);
-        const int kb_end =
-            static_cast<int>(static_cast<long long>(split + 1) * p.num_kb / p.split_k);
+      int tile, split, kb_begin, kb_end, slot;
+      for (int it = 0; get_item(it, tile, split, kb_begin, kb_end, slot); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -760,10 +851,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       if constexpr (PAIR) mbar_arrive_cluster(tmem_empty0 + acc * 8);
       else mbar_arrive(&tmem_empty[acc]);
     };
-    int it = 0;
-    for (int wi = unit; wi < total_work; wi += num_units, ++it) {
-      const int unit_tile = wi / p.split_k;
-      const int split = wi - unit_tile * p.split_k;
+    int unit_tile, split, kb_begin_, kb_end_, slot;
+    for (int it = 0; get_item(it, unit_tile, split, kb_begin_, kb_end_, slot); ++it) {
       const int m_unit = unit_tile / p.num_n_tiles;
       const int n_tile = unit_tile - m_unit * p.num_n_tiles;
       const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
@@ -779,7 +868,42 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if constexpr (!SPLIT) {
+      if constexpr (TAIL) {
+        // stream-K tail: per 128-row tail tile a run of workspace slots and one arrival counter
+        const int tt = (unit_tile - p.tail_full_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+        float* ws_tile = p.workspace + static_cast<size_t>(tt > 0 ? tt : 0) * p.tail_slots * (BM * BN);
+        if (split == 1) {
+          // a piece that ends inside the tile: publish the partial accumulator
+          epilogue_warp<BN, GEGLU, EPI_PARTIAL, NH>(ea, t_row, ws_tile, slot, m_base, n0, q, half, lane, ln_rs);
+          tc_fence_before();
+          release_acc(acc);
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread's stores before thread 0's release
+          if (et == 0) {
+            int seen;
+            asm volatile("atom.release.gpu.global.add.s32 %0, [%1], 1;" : "=r"(seen) : "l"(p.counters + tt) : "memory");
+          }
+        } else if (split == 2 && slot > 0) {
+          // the piece with the tile's last k-block: add the `slot` partials published before it
+          if (et == 0) {
+            int seen;
+            uint32_t spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tt) : "memory");
+              if (++spins > (1u << 26)) __trap();
+            } while (seen < slot);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          epilogue_warp<BN, GEGLU, EPI_DIRECT_ADD, NH>(ea, t_row, ws_tile, slot, m_base, n0, q, half, lane, ln_rs);
+          tc_fence_before();
+          release_acc(acc);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) p.counters[tt] = 0;   // re-armed for the next launch (all `slot` arrivals were consumed)
+        } else {
+          epilogue_warp<BN, GEGLU, EPI_DIRECT, NH>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane, ln_rs);
+          tc_fence_before();
+          release_acc(acc);
+        }
+      } else if constexpr (!SPLIT) {
         if (p.debug & 32) {   // development only: drop the tile (is the epilogue the bottleneck?)
           tc_fence_before();
           release_acc(acc);
@@ -1003,13 +1127,13 @@ static int validate(const ldmseg_igemm_params* p) {
   return 0;
 }
 
-template <int BN, bool GEGLU, bool SPLIT, bool PAIR>
+template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false>
 static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   using Cfg = IgemmCfg<BN, PAIR>;
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, GEGLU, SPLIT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
+    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1040,15 +1164,22 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
     static int max_clusters = 0;
     if (max_clusters == 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel<BN, GEGLU, SPLIT, PAIR>, &cfg) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = num_sms() / 2;
       }
       max_clusters = n;
     }
-    if (grid > 2 * max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+    if (grid > 2 * max_clusters) {
+      // the stream-K tail was planned for `grid` units: a smaller grid would change every unit's piece
+      if (TAIL) {
+        set_error("igemm: the device holds only %d CTA pairs at once (planned for %d)", max_clusters, grid / 2);
+        return -3;
+      }
+      cfg.gridDim = dim3(2 * max_clusters);
+    }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT, PAIR>, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL>, kp);
   if (e != cudaSuccess) {
     set_error("igemm_kernel launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
@@ -1059,6 +1190,7 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
 template <int BN, bool PAIR>
 static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   const bool geglu = kp.act == LDMSEG_ACT_GEGLU, split = kp.split_k > 1;
+  if (kp.tail) return launch_igemm_v<BN, false, false, PAIR, true>(kp, grid, stream, pdl);
   if (geglu) return split ? launch_igemm_v<BN, true, true, PAIR>(kp, grid, stream, pdl)
                           : launch_igemm_v<BN, true, false, PAIR>(kp, grid, stream, pdl);
   return split ? launch_igemm_v<BN, false, true, PAIR>(kp, grid, stream, pdl)
@@ -1194,6 +1326,28 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     kp.workspace = p->workspace;
     kp.counters = p->tile_counters;
   }
+  if (p->stream_k && kp.split_k == 1 && p->act != LDMSEG_ACT_GEGLU && bn != 64) {
+    // stream-K tail (see TailSeg): only when the last wave is ragged and its pieces are non-empty; otherwise the
+    // launch silently runs as whole tiles
+    const int units = pair ? num_sms() / 2 : num_sms();
+    const long long tiles = static_cast<long long>(pair ? (kp.num_m_tiles + 1) / 2 : kp.num_m_tiles) * kp.num_n_tiles;
+    const long long full = tiles / units * units, rem = tiles - full;
+    const long long steps = rem * num_kb;
+    if (rem > 0 && steps >= units) {
+      const long long per = steps / units;                      // shortest piece
+      const long long slots = num_kb / per + 2;                 // pieces that can touch one tile, minus the finisher
+      const long long need = rem * (pair ? 2 : 1) * slots * BM * bn;
+      if (p->workspace != nullptr && p->tile_counters != nullptr && p->workspace_elems >= need &&
+          rem * (pair ? 2 : 1) <= 4096) {
+        kp.tail = 1;
+        kp.tail_full_tiles = static_cast<int>(full);
+        kp.tail_tiles = static_cast<int>(rem);
+        kp.tail_slots = static_cast<int>(slots);
+        kp.workspace = p->workspace;
+        kp.counters = p->tile_counters;
+      }
+    }
+  }
   kp.stats = p->stats;
   kp.rowstats = p->rowstats_out;
   kp.ln_rowstats = p->ln_rowstats;
@@ -1240,7 +1394,7 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     // one CTA pair per work item, at most one pair per TPC
     const long long work = static_cast<long long>((kp.num_m_tiles + 1) / 2) * kp.num_n_tiles * kp.split_k;
     const int pairs = num_sms() / 2;
-    const int grid = 2 * static_cast<int>(work < pairs ? work : pairs);
+    const int grid = 2 * static_cast<int>((work < pairs && !kp.tail) ? work : pairs);
     switch (bn) {
       case 128: return launch_igemm<128, true>(kp, grid, st, p->pdl);
       case 160: return launch_igemm<160, true>(kp, grid, st, p->pdl);
@@ -1248,7 +1402,7 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     }
   }
   const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
-  const int grid = static_cast<int>(work < num_sms() ? work : num_sms());
+  const int grid = static_cast<int>((work < num_sms() && !kp.tail) ? work : num_sms());
   switch (bn) {
     case 64: return launch_igemm<64, false>(kp, grid, st, p->pdl);
     case 128: return launch_igemm<128, false>(kp, grid, st, p->pdl);

@@ -79,6 +79,7 @@ class IgemmParams(C.Structure):
         ("ln_colsum", C.c_void_p),
         ("ln_channels", C.c_int),
         ("ln_eps", C.c_float),
+        ("stream_k", C.c_int),
     ]
 
 
@@ -184,7 +185,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       pair: bool = False, weight_static: bool = False, out2: Optional[torch.Tensor] = None,
                       conv_stride: int = 1, conv_pad: int = 1, rowstats_out: Optional[torch.Tensor] = None,
                       ln_rowstats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None,
-                      ln_channels: int = 0, ln_eps: float = 0.0) -> IgemmParams:
+                      ln_channels: int = 0, ln_eps: float = 0.0, stream_k: bool = False) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -233,6 +234,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.ln_colsum = _ptr(ln_colsum)
     p.ln_channels = ln_channels
     p.ln_eps = ln_eps
+    p.stream_k = 1 if stream_k else 0
     return p
 
 

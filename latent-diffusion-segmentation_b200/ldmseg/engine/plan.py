@@ -30,6 +30,9 @@ NEXTW_MAX_ROWS = int(os.environ.get("LDMSEG_NEXTW_MAX_ROWS", "8192"))
 # LayerNorm folded into the GEMMs around it (row moments from the producer's epilogue, gamma / beta in the consumer's
 # weights): one launch per LayerNorm less (32 per UNet forward); 0 = separate LayerNorm kernels
 LN_FOLD = os.environ.get("LDMSEG_LN_FOLD", "1") != "0"
+# stream-K tail: the tiles past the last whole wave of a persistent grid are cut along K into one piece per CTA
+# (csrc/igemm.cu, TailSeg); 0 = ragged last waves run as whole tiles
+STREAM_K = os.environ.get("LDMSEG_STREAM_K", "1") != "0"
 
 
 USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
@@ -49,21 +52,41 @@ def _tuned_table() -> Dict[str, list]:
     return _TUNED
 
 
-def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
-                  allow_pair: bool = False, use_tuned: bool = True) -> Tuple[int, int, bool]:
-    """Pick (block_n, split_k, pair) for an igemm of M x N with num_kb 64-wide K blocks.
+# measured on B200 (profiles/r02_ablate_unet_b8_streamk_all.log against r02_ablate_unet_b8_c.log): publishing a partial
+# tile, waiting for the peers and adding their partials costs the last wave ~5.8 us whatever the tile's K: launches
+# with >= 90 k-blocks gained 15-30 %, launches with <= 45 k-blocks lost 5-20 %.  Per 160 tile columns (the partial tiles
+# cross L2 twice).
+TAIL_EXCHANGE_CYC = 11000.0
+
+
+def stream_k_shape_ok(unit_tiles: int, num_kb: int, units: int) -> bool:
+    """Shapes the stream-K tail is defined / sensible for: a ragged last wave whose K steps give every unit a
+    non-trivial piece, and -- without a whole wave before it -- pieces of at least half a tile (below that uniform
+    split-K, whose splits share the final reduction, is the better cut)."""
+    whole, rem = divmod(unit_tiles, units)
+    if rem == 0 or rem * num_kb < 4 * units:
+        return False
+    return whole > 0 or 2 * rem >= units
+
+
+def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
+                     allow_pair: bool = False, use_tuned: bool = True,
+                     allow_tail: bool = False) -> Tuple[int, int, bool, bool]:
+    """Pick (block_n, split_k, pair, stream_k_tail) for an igemm of M x N with num_kb 64-wide K blocks.
 
     Cycle model per work item (one CTA, one 128 x bn output tile, one K split):
         k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + bn))  +  prologue  +  epilogue
     items run in waves of `sms` CTAs.  A CTA pair (cta_group::2, 256 x bn tile) stages only bn/2 rows of B per CTA
-    (a measured per-k-block saving, against a fixed cluster-launch cost); it needs an even number of 128-row tiles.  Split-K (partials to a workspace, cooperative reduce) is considered
-    only when the tiles cannot fill the machine, and is charged for the partial store and the reduction."""
+    (a measured per-k-block saving, against a fixed cluster-launch cost); it needs an even number of 128-row tiles.
+    Split-K (partials to a workspace, cooperative reduce) is considered only when the tiles cannot fill the machine,
+    and is charged for the partial store and the reduction.  The stream-K tail (csrc/igemm.cu, TailSeg) replaces the
+    ragged last wave by its share of a wave plus a fixed exchange cost."""
     if use_tuned and USE_TUNED and allow_split and sms == SMS:
         hit = _tuned_table().get(f"{m},{n},{num_kb}")
         if hit is not None and (allow_pair or not hit[2]):
-            return int(hit[0]), int(hit[1]), bool(hit[2])
+            return int(hit[0]), int(hit[1]), bool(hit[2]), False
     m_tiles = (m + 127) // 128
-    best, best_cost = (128, 1, False), float("inf")
+    best, best_cost = (128, 1, False, False), float("inf")
     cands = [(bn, False) for bn in (256, 160, 128, 64)]
     # (not for short K: there the epilogue bounds the kernel and coupling two CTAs' accumulator hand-over costs
     # 10-14 %, measured at K = 320)
@@ -78,6 +101,11 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
             # ~1.5 us more -- pairs win once a CTA runs a few hundred k-blocks (batch 8: -3 % on the forward) and
             # lose in the single-wave launches of batch 1
             t_kb -= 45.0 * bn / 160.0
+        if bn != 64 and ((m_tiles + 1) // 2 if pair else m_tiles) * ((n + bn - 1) // bn) > (sms // 2 if pair else sms):
+            # multi-wave launches, measured per k-block at batch 8 under the power cap (pairs:
+            # profiles/r02_ablate_unet_b8_streamk*.log; single CTAs from the pair / single ratios of
+            # profiles/r01_bench_ingest_v11.log): the fit above is 7 % low at bn 160 and 15 % high at bn 256
+            t_kb = {128: 545.0, 160: 620.0, 256: 665.0}[bn] if pair else {128: 580.0, 160: 660.0, 256: 719.0}[bn]
         chunks = bn / 32.0
         splits = [1]
         if allow_split and tiles < sms:
@@ -85,6 +113,8 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
             while tiles * s <= sms and num_kb // s >= 4 and s <= 16:
                 splits.append(s)
                 s += 1
+        units = sms // 2 if pair else sms
+        unit_tiles = ((m_tiles + 1) // 2 if pair else m_tiles) * ((n + bn - 1) // bn)
         for s in splits:
             waves = (tiles * s + sms - 1) // sms
             kb = (num_kb + s - 1) // s
@@ -95,8 +125,24 @@ def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool
                 item += 9500 + chunks * 150
             cost = waves * item + (3000 if pair else 0)
             if cost < best_cost - 1e-9:
-                best_cost, best = cost, (bn, s, pair)
+                best_cost, best = cost, (bn, s, pair, False)
+            if s == 1 and allow_tail and bn != 64 and stream_k_shape_ok(unit_tiles, num_kb, units):
+                # tail against whole tiles for THIS tiling, with the per-launch overhead counted once (a persistent
+                # CTA pays prologue and pipeline fill once, not per wave); taken when it is worth at least 3 %, and
+                # ranked against the other tilings by scaling this tiling's whole-tile cost
+                whole, rem = divmod(unit_tiles, units)
+                plain = waves * (kb * t_kb + chunks * 120) + 9500
+                tail = (whole * (kb * t_kb + chunks * 120) + rem / units * kb * t_kb + 9500
+                        + TAIL_EXCHANGE_CYC * bn / 160.0 + chunks * 150 * (1 + min(4.0, units / rem)))
+                if tail < 0.97 * plain and cost * tail / plain < best_cost - 1e-9:
+                    best_cost, best = cost * tail / plain, (bn, 1, pair, True)
     return best
+
+
+def choose_tiling(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
+                  allow_pair: bool = False, use_tuned: bool = True) -> Tuple[int, int, bool]:
+    """(block_n, split_k, pair) without the stream-K tail (tools/tune_tiling.py, tests)."""
+    return choose_tiling_ex(m, n, num_kb, sms, allow_split, allow_pair, use_tuned, False)[:3]
 
 
 class _Layer:
@@ -220,10 +266,14 @@ class PlanBase:
         m = nb * h * w
         tiled = bool(layer.extra.get("tiled", False))
         allow_split = allow_split and self.allow_split
-        bn, split, pair = choose_tiling(m, layer.n, num_kb, allow_split=allow_split, allow_pair=USE_PAIR and tiled)
+        # the stream-K tail shares the split-K premise (a co-resident grid) and its scratch buffers
+        tail_ok = STREAM_K and allow_split and tiled and act != nat.ACT_GEGLU
+        bn, split, pair, stream_k = choose_tiling_ex(m, layer.n, num_kb, allow_split=allow_split,
+                                                     allow_pair=USE_PAIR and tiled, allow_tail=tail_ok)
         tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
         if split > 1 and tiles * split * 128 * bn > self.ws.numel():
-            bn, split, pair = choose_tiling(m, layer.n, num_kb, allow_split=False, allow_pair=USE_PAIR and tiled)
+            bn, split, pair, stream_k = choose_tiling_ex(m, layer.n, num_kb, allow_split=False,
+                                                         allow_pair=USE_PAIR and tiled, allow_tail=False)
         out_main, out2 = out, None
         if stream and self.resid_f32 and out.dtype == torch.bfloat16:
             f = self._buf(out.shape[0], out.shape[1], torch.float32)
@@ -242,12 +292,13 @@ class PlanBase:
                                   conv_stride=conv_stride, conv_pad=conv_pad, rowstats_out=rowstats,
                                   ln_rowstats=None if ln is None else ln[0],
                                   ln_colsum=None if ln is None else layer.extra["ln_colsum"],
-                                  ln_channels=0 if ln is None else ln[1], ln_eps=0.0 if ln is None else ln[2])
+                                  ln_channels=0 if ln is None else ln[1], ln_eps=0.0 if ln is None else ln[2],
+                                  stream_k=stream_k)
         self._keep.append(p)
         self._igemm_params.append((p, layer, m))
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
-        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}")
+        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}:t{int(stream_k)}")
 
     def _down(self, layer: _Layer, x, c, h, pad_lo, act=nat.ACT_NONE):
         """3x3 stride-2 convolution of x [nb*h*h, c] -> [nb*(h/2)^2, n] (a tensor of the residual stream)."""

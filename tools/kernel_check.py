@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_pair", "igemm_s2", "igemm_f32stream", "igemm_lnfold",
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_streamk", "igemm_pair", "igemm_s2", "igemm_f32stream", "igemm_lnfold",
           "gn_fused", "norm", "attn_simple", "attn", "xattn", "elementwise", "sampler", "panoptic", "vae_pdl"]
 
 
@@ -49,7 +49,7 @@ def run_group(group):
 
     def conv_case(name, nb, h, w, cin, cout, *, taps=9, bias=True, residual=False, rowbias=False,
                   act=nat.ACT_NONE, out_f32=False, block_n=0, split_k=0, simple=False, extra_src=None,
-                  shortcut=False, stats=False, pdl=False, tiled=False, pair=False):
+                  shortcut=False, stats=False, pdl=False, tiled=False, pair=False, stream_k=False):
         """out = conv(x (+ extra_src concat)) [+ 1x1 shortcut of the raw sources] ..."""
         nonlocal ok
         srcs_c = [cin] + ([extra_src] if extra_src else [])
@@ -84,16 +84,16 @@ def run_group(group):
         out = torch.full((nb * h * w, n_out), float("nan"), device=dev,
                          dtype=torch.float32 if out_f32 else bf)
         ws = cnt = None
-        if split_k > 1:
+        if split_k > 1 or stream_k:
             ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev)   # partials are overwritten, never read stale
             cnt = torch.zeros(8192, device=dev, dtype=torch.int32)
         st = torch.zeros(nb, cout, 2, device=dev) if stats else None
         p = nat.make_igemm_params(srcs, src_cs, nb, h, w, segs, wb, cout, out, n_out, bias=b,
                                   rowbias=rb, rowbias_ld=cout, residual=res, res_ld=cout, act=act,
                                   block_n=block_n, split_k=split_k, workspace=ws, counters=cnt, stats=st, pdl=pdl,
-                                  weight_tiled=tiled, pair=pair)
+                                  weight_tiled=tiled, pair=pair, stream_k=stream_k)
         nat.igemm(p, simple=simple)
-        if split_k > 1:  # second launch: tile counters must have reset themselves
+        if split_k > 1 or stream_k:  # second launch: tile counters must have reset themselves
             if st is not None:
                 st.zero_()
             nat.igemm(p, simple=simple)
@@ -124,7 +124,7 @@ def run_group(group):
             o = out.float().reshape(nb, h * w, cout)
             ok &= report(name + " [stats sum]", st[:, :, 0], o.sum(1), 1e-3)
             ok &= report(name + " [stats sumsq]", st[:, :, 1], (o * o).sum(1), 1e-3)
-        if split_k > 1:
+        if split_k > 1 or stream_k:
             ok &= report(name + " [counters reset]", cnt.float(), torch.zeros_like(cnt).float(), 0.0)
 
     if group == "simple":
@@ -211,6 +211,28 @@ def run_group(group):
                   block_n=64, stats=True, rowbias=True)
         conv_case("igemm linear geglu 256x1280->10240 split2", 1, 1, 256, 1280, 10240, taps=1, split_k=2,
                   act=nat.ACT_GEGLU)
+    elif group == "igemm_streamk":
+        # stream-K tail: ragged last waves cut along K (tiles mod 148, or mod 74 pairs)
+        conv_case("streamk conv3x3 8x64x64 320->320 bn160 (512 tiles: 3 waves + 68) +res +rowbias +stats", 8, 64, 64,
+                  320, 320, block_n=160, residual=True, rowbias=True, stats=True, tiled=True, stream_k=True)
+        conv_case("streamk pair conv3x3 8x64x64 320->320 bn160 (256 pair tiles: 3 waves + 34) +stats", 8, 64, 64,
+                  320, 320, block_n=160, stats=True, pair=True, stream_k=True)
+        conv_case("streamk conv3x3 8x32x32 640->640 bn160 (256 tiles: 1 wave + 108) silu", 8, 32, 32, 640, 640,
+                  block_n=160, act=nat.ACT_SILU, tiled=True, stream_k=True)
+        conv_case("streamk pair conv3x3 8x32x32 640->640 bn256 (96 pair tiles: 1 wave + 22) pdl", 8, 32, 32, 640,
+                  640, block_n=256, pair=True, pdl=True, stream_k=True)
+        conv_case("streamk conv3x3 8x16x16 1280->1280 bn256 (80 tiles, all tail) f32", 8, 16, 16, 1280, 1280,
+                  block_n=256, out_f32=True, tiled=True, stream_k=True)
+        conv_case("streamk conv3x3 1x64x64 320->320 bn160 (64 tiles, all tail)", 1, 64, 64, 320, 320, block_n=160,
+                  tiled=True, stream_k=True)
+        conv_case("streamk linear 8192x1280->1280 bn128 (640 tiles: 4 waves + 48)", 1, 1, 8192, 1280, 1280, taps=1,
+                  block_n=128, tiled=True, stream_k=True)
+        conv_case("streamk pair linear 4224x1280->640 bn128 (odd m tiles, phantom)", 1, 1, 4224, 1280, 640, taps=1,
+                  block_n=128, pair=True, stream_k=True)
+        conv_case("streamk conv3x3 dual + 1x1 shortcut 8x32x32 bn160", 8, 32, 32, 640, 640, extra_src=320,
+                  shortcut=True, block_n=160, tiled=True, stream_k=True)
+        conv_case("streamk full last wave falls back to whole tiles (296 tiles)", 1, 1, 9472, 640, 512, taps=1,
+                  block_n=128, tiled=True, stream_k=True)
     elif group == "igemm_pair":
         # CTA pairs (cta_group::2): 256 x block_n tiles
         for bn in (128, 160, 256):
