@@ -128,9 +128,18 @@ typedef struct ldmseg_igemm_params {
                                         go through `workspace` / `tile_counters` (same buffers as split_k, which must
                                         be 0/1) and the CTA holding a tile's last k-block finishes it.  Ignored (whole
                                         tiles) when the last wave is full, for GEGLU and for block_n 64 */
+  int split_cluster;                 /* 1 (with split_k > 1, not with pair): launch the split_k CTAs of every tile as one
+                                        thread-block cluster and exchange the partial tiles through distributed shared
+                                        memory instead of `workspace` (which is then unused).  Falls back to the
+                                        workspace exchange when the device cannot hold all the tiles' clusters at once
+                                        (see ldmseg_igemm_max_split_clusters) */
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);
+
+/* Number of clusters of `cluster_size` (2..16) split-K CTAs of the given tile width the device holds at once; a split
+ * launch with split_cluster needs tiles <= this.  0 when such clusters cannot be scheduled.  Needs a CUDA device. */
+int ldmseg_igemm_max_split_clusters(int block_n, int geglu, int cluster_size);
 
 /* Reference-grade CUDA-core version of the same contract (fp32 accumulate, no tensor cores).
  * Test infrastructure for the tcgen05 kernel -- never on the product path. */

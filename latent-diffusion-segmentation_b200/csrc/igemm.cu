@@ -75,6 +75,8 @@ struct alignas(64) IgemmKParams {
   int w_tiled;        // weights stored as [N/16][K/64][16][64] blocks (2 KB contiguous per block)
   int coop_reduce;    // split-K: all epilogue warps share the reduction of each owned chunk (see splitk_final_coop)
   int prefetch_b;     // issue the first work item's weight loads before the grid-dependency wait
+  int csplit;          // split-K inside a thread-block cluster: the splits of a tile exchange partials through
+                       // distributed shared memory (see splitk_final_cluster)
   int tail;            // stream-K tail (see TailSeg): tiles [0, tail_full_tiles) run whole, in waves of the grid; the
   int tail_full_tiles; // tail_tiles after them are cut along K into one contiguous piece per CTA
   int tail_tiles;
@@ -532,6 +534,117 @@ __device__ __forceinline__ void splitk_final_coop(const EpiArgs& p, const float*
   }
 }
 
+// ---- split-K through distributed shared memory ---------------------------------------------------
+// The S split CTAs of a tile are launched as one thread-block cluster (cluster rank = split index).  The tile's
+// 4 x BN/32 (row quadrant, 32-column chunk) units are dealt round-robin to the splits; every CTA PUSHES each unit of
+// its partial accumulator straight from TMEM into the shared memory of the unit's owner (st.shared::cluster, 512
+// contiguous bytes per warp instruction, fire and forget), the cluster meets at a hardware barrier, and every owner
+// sums its units' S slots out of its OWN shared memory and finishes them.  The operand ring is idle by then (a split
+// launch gives every CTA exactly one work item).  Against the global-memory exchange above (partial tile to L2, release
+// atomic, acquire spin, partials back from L2, counter re-arm: three dependent L2 round trips plus a gpu-scope
+// release, measured in-graph at batch 1 as 7.6 us per split launch, 17 % of the UNet forward -- tools/ablate_unet.py
+// with LDMSEG_DEBUG_FLAGS=1/2/6) nothing leaves the cluster and nothing waits on a remote load.  (Pulling the partials
+// with ld.shared::cluster instead cost 3 us per launch in exposed latency, 12 us with a row-major slot layout whose
+// loads were 32 separate 16-byte requests.)
+// Slot layout in the owner's shared memory: [own unit k][split s][16-byte piece g 0..7][row 0..31][4 f32].
+__device__ __forceinline__ uint32_t csplit_slot(uint32_t part_u32, int k, int s, int S, int lane) {
+  return part_u32 + static_cast<uint32_t>(((k * S + s) * 8) * 512 + lane * 16);
+}
+template <int BN, bool GEGLU>
+__device__ __forceinline__ void splitk_final_cluster(const EpiArgs& p, uint32_t part_u32, int S, int split_idx,
+                                                     int tile_m0, int n0, int ew, int lane, float* stage, int debug) {
+  constexpr int kChunks = BN / 32;
+  constexpr int kUnits = 4 * kChunks;
+  const int n_own = (kUnits - split_idx + S - 1) / S;
+  if (n_own <= 0) return;
+  int T = 8;
+  while (T > 1 && T * n_own > 8) T >>= 1;
+  const int n_teams = 8 / T, team = ew / T, j = ew - team * T;
+  float4* st4 = reinterpret_cast<float4*>(stage);   // [warp][8 float4 groups][32 lanes]
+  for (int k = team; k < n_own; k += n_teams) {
+    const int u = split_idx + k * S;
+    const int q = u / kChunks, ch = u - q * kChunks;
+    const int col0 = n0 + ch * 32;
+    const bool live = col0 < p.N;
+    const int row = q * 32 + lane;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    if (live && tile_m0 + row < p.M && !(debug & 1)) {
+#pragma unroll 2
+      for (int s = j; s < S; s += T) {
+        const uint32_t slot = csplit_slot(part_u32, k, s, S, lane);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 a;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                       : "r"(slot + static_cast<uint32_t>(g * 512))
+                       : "memory");
+          v[4 * g] += a.x; v[4 * g + 1] += a.y; v[4 * g + 2] += a.z; v[4 * g + 3] += a.w;
+        }
+      }
+    }
+    if (T > 1) {
+      if (j != 0) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          st4[(ew * 8 + g) * 32 + lane] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(T * 32) : "memory");
+      if (j == 0) {
+        for (int jj = 1; jj < T; ++jj) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 a = st4[((ew + jj) * 8 + g) * 32 + lane];
+            v[4 * g] += a.x; v[4 * g + 1] += a.y; v[4 * g + 2] += a.z; v[4 * g + 3] += a.w;
+          }
+        }
+      }
+      // the team's staging slices are rewritten by its next unit
+      if (k + n_teams < n_own) asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(T * 32) : "memory");
+    }
+    if (j == 0 && live) {
+      const int m = tile_m0 + row;
+      float ln_mu = 0.f, ln_r = 1.f, rs1 = 0.f, rs2 = 0.f;
+      if (p.ln_rowstats != nullptr && m < p.M) {
+        const float2 rs = __ldcg(reinterpret_cast<const float2*>(p.ln_rowstats) + m);
+        ln_mu = rs.x * p.ln_inv_c;
+        ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, rs.y * p.ln_inv_c), 0.f) + p.ln_eps);
+      }
+      epi_finish<GEGLU>(p, v, m, m / p.HW, (tile_m0 + q * 32) / p.stats_hw, col0, lane, ln_mu, ln_r, rs1, rs2);
+      if constexpr (!GEGLU) {
+        if (p.rowstats != nullptr && m < p.M) {
+          atomicAdd(p.rowstats + 2 * static_cast<size_t>(m), rs1);
+          atomicAdd(p.rowstats + 2 * static_cast<size_t>(m) + 1, rs2);
+        }
+      }
+    }
+  }
+}
+// Pull the epilogue operands of the units this CTA will finish towards the SM while the MMAs are still running: the
+// final pass is a chain of short dependent steps and every L2 round trip in it is exposed.
+template <int BN>
+__device__ __forceinline__ void csplit_prefetch_epilogue(const EpiArgs& p, int S, int split_idx, int tile_m0, int n0,
+                                                         int ew, int lane) {
+  constexpr int kChunks = BN / 32;
+  constexpr int kUnits = 4 * kChunks;
+  for (int u = split_idx + ew * S; u < kUnits; u += 8 * S) {
+    const int q = u / kChunks, ch = u - q * kChunks;
+    const int col0 = n0 + ch * 32;
+    const int m = tile_m0 + q * 32 + lane;
+    if (col0 >= p.N || m >= p.M) continue;
+    if (p.residual != nullptr)
+      prefetch_l1(reinterpret_cast<const uint8_t*>(p.residual) +
+                  (static_cast<size_t>(m) * p.res_ld + col0) * (p.res_f32 ? 4 : 2));
+    if (lane == 0) {
+      if (p.bias != nullptr) prefetch_l1(p.bias + col0);
+      if (p.rowbias != nullptr) prefetch_l1(p.rowbias + static_cast<size_t>(m / p.HW) * p.rowbias_ld + col0);
+      if (p.ln_colsum != nullptr) prefetch_l1(p.ln_colsum + col0);
+    }
+  }
+}
+
 // ---- stream-K tail ---------------------------------------------------------------------------
 // A persistent grid of G units (CTAs, or CTA pairs) runs T tiles in ceil(T / G) waves; the last wave is only
 // (T mod G) / G full (N = 320 at a 64x64 latent, batch 8: 512 tiles on 148 SMs = 3.46 waves paid as 4; 256 tiles as 2).
@@ -577,10 +690,11 @@ __device__ __forceinline__ int tail_plan(int tail_full_tiles, int tail_tiles, in
   return 2;
 }
 
-template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false>
+template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false, bool CSPLIT = false>
 __global__ void __launch_bounds__(igemm_threads(GEGLU, SPLIT), 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
   static_assert(!(TAIL && (SPLIT || GEGLU)), "the stream-K tail replaces split-K; it is not built for GEGLU");
+  static_assert(!CSPLIT || (SPLIT && !PAIR && !TAIL), "the cluster exchange is a form of split-K for single CTAs");
   using Cfg = IgemmCfg<BN, PAIR>;
   constexpr int kEpiWarps = igemm_epi_warps(GEGLU, SPLIT);
   constexpr int kEpiThreads = kEpiWarps * 32;
@@ -786,6 +900,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       }
     }
     __syncwarp();
+    if constexpr (CSPLIT) {   // barriers 1 and 2 of 3 (see the epilogue warps)
+      cluster_sync_all();
+      cluster_sync_all();
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if ((!PAIR || rank == 0) && elect_one()) {
@@ -832,6 +950,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       }
     }
     __syncwarp();
+    if constexpr (CSPLIT) {   // barriers 1 and 2 of 3
+      cluster_sync_all();
+      cluster_sync_all();
+    }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     pdl_wait();
@@ -865,10 +987,49 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       float2 ln_rs = make_float2(0.f, 1.f);
       if (ea.ln_rowstats != nullptr && m_base + lane < ea.M)
         ln_rs = __ldcg(reinterpret_cast<const float2*>(ea.ln_rowstats) + m_base + lane);
+      if constexpr (CSPLIT) csplit_prefetch_epilogue<BN>(ea, p.split_k, split, m_tile * BM, n0, warp - 2, lane);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if constexpr (TAIL) {
+      if constexpr (CSPLIT) {
+        // split-K inside a cluster (one work item per CTA; cluster rank = split): every unit of the partial goes to
+        // the shared memory of the split that owns the unit
+        const uint32_t part_u32 = smem_u32(smem_a);
+        constexpr int kChunksC = BN / 32;
+        const int S = p.split_k;
+        // barrier 1 of 3: this CTA's MMAs are done (tmem_full), its operand ring may be overwritten; nobody pushes
+        // before every CTA of the cluster has said so (a fast split would otherwise write into a ring its slower
+        // peer is still multiplying from).  Arrive now, wait just before the first remote store.
+        cluster_arrive();
+        bool waited = false;
+#pragma unroll 1
+        for (int ch = half; ch < kChunksC; ch += NH) {
+          if (n0 + ch * 32 >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + ch * 32, r);
+          tmem_wait_ld();
+          if (!waited) {
+            cluster_wait();
+            waited = true;
+          }
+          const int u = q * kChunksC + ch;
+          const int owner = u % S, k_own = u / S;
+          uint32_t dst;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                       : "=r"(dst)
+                       : "r"(csplit_slot(part_u32, k_own, split, S, lane)), "r"(static_cast<uint32_t>(owner)));
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            st_dsmem_b4(dst + static_cast<uint32_t>(g * 512), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+        }
+        if (!waited) cluster_wait();
+        tc_fence_before();
+        release_acc(acc);
+        cluster_sync_all();   // barrier 2 of 3 (release / acquire: every split's pushes have landed)
+        if (!(p.debug & 2))   // debug bit1: no final pass
+          splitk_final_cluster<BN, GEGLU>(ea, part_u32, S, split, m_tile * BM, n0, warp - 2, lane,
+                                          reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes - 32768), p.debug);
+      } else if constexpr (TAIL) {
         // stream-K tail: per 128-row tail tile a run of workspace slots and one arrival counter
         const int tt = (unit_tile - p.tail_full_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
         float* ws_tile = p.workspace + static_cast<size_t>(tt > 0 ? tt : 0) * p.tail_slots * (BM * BN);
@@ -961,7 +1122,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   }
 
   tc_fence_before();
-  if constexpr (PAIR) cluster_sync_all();   // the peer may still signal this CTA's barriers / read its operands
+  // (CSPLIT: barrier 3 of 3 -- no CTA of a cluster exits while barrier traffic or pushes could still target it)
+  if constexpr (PAIR || CSPLIT) cluster_sync_all();   // the peer may still signal this CTA's barriers / read its operands
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -1127,13 +1289,14 @@ static int validate(const ldmseg_igemm_params* p) {
   return 0;
 }
 
-template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false>
+template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false, bool CSPLIT = false>
 static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   using Cfg = IgemmCfg<BN, PAIR>;
+  auto kernel = igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL, CSPLIT>;
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    LDM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (CSPLIT) LDM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1144,9 +1307,10 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (PAIR) {   // the two CTAs of a pair must share a TPC: cluster of 2 along x
+  const bool dbg_cluster = !PAIR && !CSPLIT && SPLIT && (g_debug & 64) && grid % kp.split_k == 0 && kp.split_k <= 8;
+  if (PAIR || CSPLIT || dbg_cluster) {   // the two CTAs of a pair must share a TPC; the splits of a tile form one cluster
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.x = (CSPLIT || dbg_cluster) ? kp.split_k : 2;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -1164,7 +1328,7 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
     static int max_clusters = 0;
     if (max_clusters == 0) {
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL>, &cfg) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = num_sms() / 2;
       }
@@ -1179,7 +1343,7 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
       cfg.gridDim = dim3(2 * max_clusters);
     }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel<BN, GEGLU, SPLIT, PAIR, TAIL>, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, kp);
   if (e != cudaSuccess) {
     set_error("igemm_kernel launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
@@ -1187,10 +1351,64 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   return check_launch("igemm_kernel");
 }
 
+// How many clusters of `cluster_size` split CTAs the device holds at once (0: such a cluster cannot be formed).  A
+// split launch is a single wave by construction, so its tile count must not exceed this.
+template <int BN, bool GEGLU>
+static int csplit_max_clusters_v(int cluster_size) {
+  using Cfg = IgemmCfg<BN, false>;
+  auto kernel = igemm_kernel<BN, GEGLU, true, false, false, true>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cluster_size * num_sms());
+  cfg.blockDim = dim3(igemm_threads(GEGLU, true));
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+static int csplit_max_clusters(int bn, bool geglu, int cluster_size) {
+  if (cluster_size < 2 || cluster_size > 16) return 0;
+  static int cache[4][2][17];
+  static bool have[4][2][17];
+  const int bi = bn == 64 ? 0 : bn == 128 ? 1 : bn == 160 ? 2 : 3;
+  if (!have[bi][geglu][cluster_size]) {
+    int n = 0;
+    switch (bn) {
+      case 64: n = geglu ? csplit_max_clusters_v<64, true>(cluster_size) : csplit_max_clusters_v<64, false>(cluster_size); break;
+      case 128: n = geglu ? csplit_max_clusters_v<128, true>(cluster_size) : csplit_max_clusters_v<128, false>(cluster_size); break;
+      case 160: n = geglu ? csplit_max_clusters_v<160, true>(cluster_size) : csplit_max_clusters_v<160, false>(cluster_size); break;
+      default: n = geglu ? csplit_max_clusters_v<256, true>(cluster_size) : csplit_max_clusters_v<256, false>(cluster_size); break;
+    }
+    cache[bi][geglu][cluster_size] = n;
+    have[bi][geglu][cluster_size] = true;
+  }
+  return cache[bi][geglu][cluster_size];
+}
+
 template <int BN, bool PAIR>
 static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   const bool geglu = kp.act == LDMSEG_ACT_GEGLU, split = kp.split_k > 1;
   if (kp.tail) return launch_igemm_v<BN, false, false, PAIR, true>(kp, grid, stream, pdl);
+  if constexpr (!PAIR) {
+    if (kp.csplit)
+      return geglu ? launch_igemm_v<BN, true, true, false, false, true>(kp, grid, stream, pdl)
+                   : launch_igemm_v<BN, false, true, false, false, true>(kp, grid, stream, pdl);
+  }
   if (geglu) return split ? launch_igemm_v<BN, true, true, PAIR>(kp, grid, stream, pdl)
                           : launch_igemm_v<BN, true, false, PAIR>(kp, grid, stream, pdl);
   return split ? launch_igemm_v<BN, false, true, PAIR>(kp, grid, stream, pdl)
@@ -1326,6 +1544,17 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     kp.workspace = p->workspace;
     kp.counters = p->tile_counters;
   }
+  if (p->split_cluster && kp.split_k > 1 && !pair) {
+    // the splits of a tile as one cluster: only if every tile's cluster fits on the device at once
+    const long long tiles = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles;
+    // the owner's slots ([own units][splits] x 4 KB) and 32 KB of staging must fit in the idle operand ring
+    const int units = 4 * bn / 32, n_own = (units + kp.split_k - 1) / kp.split_k;
+    const long long ring = bn == 64 ? 9LL * (kABytes + 64 * 128) : bn == 128 ? 7LL * (kABytes + 128 * 128)
+                           : bn == 160 ? 6LL * (kABytes + 160 * 128) : 4LL * (kABytes + 256 * 128);
+    if (static_cast<long long>(n_own) * kp.split_k * 4096 + 32768 <= ring &&
+        tiles <= csplit_max_clusters(bn, p->act == LDMSEG_ACT_GEGLU, kp.split_k))
+      kp.csplit = 1;
+  }
   if (p->stream_k && kp.split_k == 1 && p->act != LDMSEG_ACT_GEGLU && bn != 64) {
     // stream-K tail (see TailSeg): only when the last wave is ragged and its pieces are non-empty; otherwise the
     // launch silently runs as whole tiles
@@ -1402,13 +1631,18 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     }
   }
   const long long work = static_cast<long long>(kp.num_m_tiles) * kp.num_n_tiles * kp.split_k;
-  const int grid = static_cast<int>((work < num_sms() && !kp.tail) ? work : num_sms());
+  const int grid = static_cast<int>(((work < num_sms() && !kp.tail) || kp.csplit) ? work : num_sms());
   switch (bn) {
     case 64: return launch_igemm<64, false>(kp, grid, st, p->pdl);
     case 128: return launch_igemm<128, false>(kp, grid, st, p->pdl);
     case 160: return launch_igemm<160, false>(kp, grid, st, p->pdl);
     default: return launch_igemm<256, false>(kp, grid, st, p->pdl);
   }
+}
+
+extern "C" int ldmseg_igemm_max_split_clusters(int block_n, int geglu, int cluster_size) {
+  if (block_n != 64 && block_n != 128 && block_n != 160 && block_n != 256) return 0;
+  return csplit_max_clusters(block_n, geglu != 0, cluster_size);
 }
 
 extern "C" int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream) {

@@ -31,7 +31,7 @@ EXPORTS = [
     "ldmseg_bilinear2x_argmax", "ldmseg_select_row", "ldmseg_ddim_step_indexed", "ldmseg_softmax_rows", "ldmseg_nchw_f32_to_nhwc",
     "ldmseg_groupnorm_apply_cs", "ldmseg_set_pdl", "ldmseg_set_debug",
     "ldmseg_groupnorm_apply_cs_f32", "ldmseg_layernorm_f32", "ldmseg_noise_mix", "ldmseg_cross_attention",
-    "ldmseg_panoptic_resample", "ldmseg_panoptic_filter",
+    "ldmseg_panoptic_resample", "ldmseg_panoptic_filter", "ldmseg_igemm_max_split_clusters",
 ]
 
 
@@ -80,6 +80,7 @@ class IgemmParams(C.Structure):
         ("ln_channels", C.c_int),
         ("ln_eps", C.c_float),
         ("stream_k", C.c_int),
+        ("split_cluster", C.c_int),
     ]
 
 
@@ -135,6 +136,7 @@ def load() -> C.CDLL:
         "ldmseg_select_row": [vp, i32, vp, i32, vp, vp],
         "ldmseg_groupnorm_apply_cs": [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, vp, vp],
         "ldmseg_set_pdl": [i32],
+        "ldmseg_igemm_max_split_clusters": [i32, i32, i32],
         "ldmseg_set_debug": [i32],
         "ldmseg_softmax_rows": [vp, i32, i32, f32, vp, vp],
         "ldmseg_ddim_step_indexed": [vp, vp, i64, vp, vp, i32, f32, i32, i32, f32, i32, vp, vp, vp],
@@ -169,6 +171,20 @@ def require_cuda(*tensors: torch.Tensor) -> None:
                 "There is deliberately no CPU fallback.")
 
 
+_split_cluster_cap = {}
+
+
+def max_split_clusters(block_n: int, geglu: bool, cluster_size: int) -> int:
+    """Clusters of `cluster_size` split-K CTAs the device holds at once (0 without a CUDA device)."""
+    key = (block_n, bool(geglu), cluster_size)
+    if key not in _split_cluster_cap:
+        n = 0
+        if torch.cuda.is_available():
+            n = int(load().ldmseg_igemm_max_split_clusters(block_n, 1 if geglu else 0, cluster_size))
+        _split_cluster_cap[key] = max(n, 0)
+    return _split_cluster_cap[key]
+
+
 def launch_count() -> int:
     return int(load().ldmseg_launch_count())
 
@@ -185,7 +201,8 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       pair: bool = False, weight_static: bool = False, out2: Optional[torch.Tensor] = None,
                       conv_stride: int = 1, conv_pad: int = 1, rowstats_out: Optional[torch.Tensor] = None,
                       ln_rowstats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None,
-                      ln_channels: int = 0, ln_eps: float = 0.0, stream_k: bool = False) -> IgemmParams:
+                      ln_channels: int = 0, ln_eps: float = 0.0, stream_k: bool = False,
+                      split_cluster: bool = False) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -235,6 +252,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.ln_channels = ln_channels
     p.ln_eps = ln_eps
     p.stream_k = 1 if stream_k else 0
+    p.split_cluster = 1 if split_cluster else 0
     return p
 
 

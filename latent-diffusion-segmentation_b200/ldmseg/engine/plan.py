@@ -33,6 +33,12 @@ LN_FOLD = os.environ.get("LDMSEG_LN_FOLD", "1") != "0"
 # stream-K tail: the tiles past the last whole wave of a persistent grid are cut along K into one piece per CTA
 # (csrc/igemm.cu, TailSeg); 0 = ragged last waves run as whole tiles
 STREAM_K = os.environ.get("LDMSEG_STREAM_K", "1") != "0"
+# split-K exchange through distributed shared memory (the splits of a tile launched as one thread-block cluster, every
+# unit of the partial tile pushed into its owner's shared memory) wherever the device can hold all the tiles' clusters
+# at once.  OFF by default: measured in-graph at batch 1 it is no faster than the global workspace (2793 vs 2756 us per
+# UNet forward; profiles/r02_ab_cluster_splitk.log) -- moving a 64-128 KB fp32 partial tile per CTA over the SM-to-SM
+# network takes ~3 us, as long as the three L2 round trips it replaces; 1 = use it
+SPLIT_CLUSTER = os.environ.get("LDMSEG_SPLIT_CLUSTER", "0") != "0"
 
 
 USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
@@ -69,10 +75,17 @@ def stream_k_shape_ok(unit_tiles: int, num_kb: int, units: int) -> bool:
     return whole > 0 or 2 * rem >= units
 
 
+# cycles of the split-K exchange per launch: through the global workspace (partial tile to L2, release atomic, acquire
+# spin, partials back, counter re-arm; measured in-graph at batch 1 as 7.6 us per launch) and inside a cluster
+SPLIT_EXCHANGE_CYC = 9500.0
+CSPLIT_EXCHANGE_CYC = 3500.0
+
+
 def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
-                     allow_pair: bool = False, use_tuned: bool = True,
-                     allow_tail: bool = False) -> Tuple[int, int, bool, bool]:
-    """Pick (block_n, split_k, pair, stream_k_tail) for an igemm of M x N with num_kb 64-wide K blocks.
+                     allow_pair: bool = False, use_tuned: bool = True, allow_tail: bool = False,
+                     cluster_cap: Optional[Callable[[int, int], int]] = None) -> Tuple[int, int, bool, bool, bool]:
+    """Pick (block_n, split_k, pair, stream_k_tail, split_cluster) for an igemm of M x N with num_kb 64-wide K blocks.
+    `cluster_cap(block_n, split)`: how many clusters of `split` CTAs the device holds at once (None: no clusters).
 
     Cycle model per work item (one CTA, one 128 x bn output tile, one K split):
         k-blocks * max(MMA = 4 * bn/2, ingest = 2.17 * (128 + bn))  +  prologue  +  epilogue
@@ -84,9 +97,12 @@ def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: b
     if use_tuned and USE_TUNED and allow_split and sms == SMS:
         hit = _tuned_table().get(f"{m},{n},{num_kb}")
         if hit is not None and (allow_pair or not hit[2]):
-            return int(hit[0]), int(hit[1]), bool(hit[2]), False
+            bn, s, pair = int(hit[0]), int(hit[1]), bool(hit[2])
+            tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+            clus = bool(s > 1 and not pair and cluster_cap is not None and tiles <= cluster_cap(bn, s))
+            return bn, s, pair, False, clus
     m_tiles = (m + 127) // 128
-    best, best_cost = (128, 1, False, False), float("inf")
+    best, best_cost = (128, 1, False, False, False), float("inf")
     cands = [(bn, False) for bn in (256, 160, 128, 64)]
     # (not for short K: there the epilogue bounds the kernel and coupling two CTAs' accumulator hand-over costs
     # 10-14 %, measured at K = 320)
@@ -121,11 +137,13 @@ def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: b
             # measured (tools/bench_split.py, bench_epi.py): ~5 us of launch + prologue + pipeline fill + epilogue
             # tail per wave, ~5 us more for the split-K publish / wait-for-peers / reduce pass
             item = kb * t_kb + 9500 + chunks * 120
+            clus = False
             if s > 1:
-                item += 9500 + chunks * 150
+                clus = bool(not pair and cluster_cap is not None and tiles <= cluster_cap(bn, s))
+                item += (CSPLIT_EXCHANGE_CYC if clus else SPLIT_EXCHANGE_CYC) + chunks * 150
             cost = waves * item + (3000 if pair else 0)
             if cost < best_cost - 1e-9:
-                best_cost, best = cost, (bn, s, pair, False)
+                best_cost, best = cost, (bn, s, pair, False, clus)
             if s == 1 and allow_tail and bn != 64 and stream_k_shape_ok(unit_tiles, num_kb, units):
                 # tail against whole tiles for THIS tiling, with the per-launch overhead counted once (a persistent
                 # CTA pays prologue and pipeline fill once, not per wave); taken when it is worth at least 3 %, and
@@ -135,7 +153,7 @@ def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: b
                 tail = (whole * (kb * t_kb + chunks * 120) + rem / units * kb * t_kb + 9500
                         + TAIL_EXCHANGE_CYC * bn / 160.0 + chunks * 150 * (1 + min(4.0, units / rem)))
                 if tail < 0.97 * plain and cost * tail / plain < best_cost - 1e-9:
-                    best_cost, best = cost * tail / plain, (bn, 1, pair, True)
+                    best_cost, best = cost * tail / plain, (bn, 1, pair, True, False)
     return best
 
 
@@ -268,12 +286,15 @@ class PlanBase:
         allow_split = allow_split and self.allow_split
         # the stream-K tail shares the split-K premise (a co-resident grid) and its scratch buffers
         tail_ok = STREAM_K and allow_split and tiled and act != nat.ACT_GEGLU
-        bn, split, pair, stream_k = choose_tiling_ex(m, layer.n, num_kb, allow_split=allow_split,
-                                                     allow_pair=USE_PAIR and tiled, allow_tail=tail_ok)
+        geglu = act == nat.ACT_GEGLU
+        cap = (lambda bn_, s_: nat.max_split_clusters(bn_, geglu, s_)) if SPLIT_CLUSTER and allow_split else None
+        bn, split, pair, stream_k, split_cluster = choose_tiling_ex(
+            m, layer.n, num_kb, allow_split=allow_split, allow_pair=USE_PAIR and tiled, allow_tail=tail_ok,
+            cluster_cap=cap)
         tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
-        if split > 1 and tiles * split * 128 * bn > self.ws.numel():
-            bn, split, pair, stream_k = choose_tiling_ex(m, layer.n, num_kb, allow_split=False,
-                                                         allow_pair=USE_PAIR and tiled, allow_tail=False)
+        if split > 1 and not split_cluster and tiles * split * 128 * bn > self.ws.numel():
+            bn, split, pair, stream_k, split_cluster = choose_tiling_ex(
+                m, layer.n, num_kb, allow_split=False, allow_pair=USE_PAIR and tiled, allow_tail=False)
         out_main, out2 = out, None
         if stream and self.resid_f32 and out.dtype == torch.bfloat16:
             f = self._buf(out.shape[0], out.shape[1], torch.float32)
@@ -293,12 +314,12 @@ class PlanBase:
                                   ln_rowstats=None if ln is None else ln[0],
                                   ln_colsum=None if ln is None else layer.extra["ln_colsum"],
                                   ln_channels=0 if ln is None else ln[1], ln_eps=0.0 if ln is None else ln[2],
-                                  stream_k=stream_k)
+                                  stream_k=stream_k, split_cluster=split_cluster)
         self._keep.append(p)
         self._igemm_params.append((p, layer, m))
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
-        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}:t{int(stream_k)}")
+        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}:t{int(stream_k)}:c{int(split_cluster)}")
 
     def _down(self, layer: _Layer, x, c, h, pad_lo, act=nat.ACT_NONE):
         """3x3 stride-2 convolution of x [nb*h*h, c] -> [nb*(h/2)^2, n] (a tensor of the residual stream)."""

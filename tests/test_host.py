@@ -32,7 +32,7 @@ def test_igemm_params_struct_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_0-9]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
     fields = [f[0] for f in nat.IgemmParams._fields_]
-    assert fields == names and len(fields) == 45
+    assert fields == names and len(fields) == 46
 
 
 def test_product_scheduler_host_logic_matches_reference(golden_dir):

@@ -49,6 +49,8 @@ def main():
     args = ap.parse_args()
     from bench import build_models
     from ldmseg import _native as nat
+    if os.environ.get("LDMSEG_DEBUG_FLAGS"):   # igemm timing experiments (garbage results), see IgemmKParams.debug
+        nat.load().ldmseg_set_debug(int(os.environ["LDMSEG_DEBUG_FLAGS"]))
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     unet, _, _, _ = build_models(dev)

@@ -49,7 +49,7 @@ def run_group(group):
 
     def conv_case(name, nb, h, w, cin, cout, *, taps=9, bias=True, residual=False, rowbias=False,
                   act=nat.ACT_NONE, out_f32=False, block_n=0, split_k=0, simple=False, extra_src=None,
-                  shortcut=False, stats=False, pdl=False, tiled=False, pair=False, stream_k=False):
+                  shortcut=False, stats=False, pdl=False, tiled=False, pair=False, stream_k=False, split_cluster=False):
         """out = conv(x (+ extra_src concat)) [+ 1x1 shortcut of the raw sources] ..."""
         nonlocal ok
         srcs_c = [cin] + ([extra_src] if extra_src else [])
@@ -91,7 +91,7 @@ def run_group(group):
         p = nat.make_igemm_params(srcs, src_cs, nb, h, w, segs, wb, cout, out, n_out, bias=b,
                                   rowbias=rb, rowbias_ld=cout, residual=res, res_ld=cout, act=act,
                                   block_n=block_n, split_k=split_k, workspace=ws, counters=cnt, stats=st, pdl=pdl,
-                                  weight_tiled=tiled, pair=pair, stream_k=stream_k)
+                                  weight_tiled=tiled, pair=pair, stream_k=stream_k, split_cluster=split_cluster)
         nat.igemm(p, simple=simple)
         if split_k > 1 or stream_k:  # second launch: tile counters must have reset themselves
             if st is not None:
@@ -211,6 +211,29 @@ def run_group(group):
                   block_n=64, stats=True, rowbias=True)
         conv_case("igemm linear geglu 256x1280->10240 split2", 1, 1, 256, 1280, 10240, taps=1, split_k=2,
                   act=nat.ACT_GEGLU)
+        # the same exchange through distributed shared memory (the splits of a tile = one cluster)
+        for s_ in (2, 3, 4, 5, 6, 7, 8, 9, 12, 14, 16):
+            print(f"max clusters of {s_}: bn64 {nat.max_split_clusters(64, False, s_)} bn128 "
+                  f"{nat.max_split_clusters(128, False, s_)} bn160 {nat.max_split_clusters(160, False, s_)} bn256 "
+                  f"{nat.max_split_clusters(256, False, s_)} geglu bn256 {nat.max_split_clusters(256, True, s_)}")
+        conv_case("cluster split conv3x3 1x8x8 1280->1280 split4 bn128", 1, 8, 8, 1280, 1280, split_k=4, block_n=128,
+                  split_cluster=True, tiled=True)
+        conv_case("cluster split conv3x3 1x16x16 1280->1280 split9 bn160 +res", 1, 16, 16, 1280, 1280, split_k=9,
+                  block_n=160, residual=True, split_cluster=True, tiled=True)
+        conv_case("cluster split linear 256x1280->1280 split3 bn256 silu", 1, 1, 256, 1280, 1280, taps=1, split_k=3,
+                  block_n=256, act=nat.ACT_SILU, split_cluster=True, tiled=True)
+        conv_case("cluster split conv3x3 1x8x8 1280->1280 split6 bn64 +stats +rowbias", 1, 8, 8, 1280, 1280,
+                  split_k=6, block_n=64, stats=True, rowbias=True, split_cluster=True, tiled=True)
+        conv_case("cluster split conv3x3 1x64x64 320->320 split2 bn160 pdl", 1, 64, 64, 320, 320, split_k=2,
+                  block_n=160, pdl=True, split_cluster=True, tiled=True)
+        conv_case("cluster split conv3x3 1x32x32 640->640 split5 bn256 f32", 1, 32, 32, 640, 640, split_k=5,
+                  block_n=256, out_f32=True, split_cluster=True, tiled=True)
+        conv_case("cluster split linear geglu 256x1280->10240 split2 bn256", 1, 1, 256, 1280, 10240, taps=1,
+                  split_k=2, block_n=256, act=nat.ACT_GEGLU, split_cluster=True, tiled=True)
+        conv_case("cluster split conv3x3 1x8x8 1280->1280 split14 bn128 (falls back unless 10 clusters of 14 fit)",
+                  1, 8, 8, 1280, 1280, split_k=14, block_n=128, split_cluster=True, tiled=True)
+        conv_case("cluster split conv3x3 dual + 1x1 shortcut 1x16x16 split8 bn160", 1, 16, 16, 1280, 640,
+                  extra_src=640, shortcut=True, split_k=8, block_n=160, split_cluster=True, tiled=True)
     elif group == "igemm_streamk":
         # stream-K tail: ragged last waves cut along K (tiles mod 148, or mod 74 pairs)
         conv_case("streamk conv3x3 8x64x64 320->320 bn160 (512 tiles: 3 waves + 68) +res +rowbias +stats", 8, 64, 64,
