@@ -465,6 +465,11 @@ __device__ __forceinline__ float ex2_approx_f(float x) {
   return y;
 }
 
+// Two adjacent floats added in one L2 reduction (8-byte aligned address, no return value).
+__device__ __forceinline__ void red_add_f32x2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
