@@ -337,9 +337,21 @@ def kernel_roofline(plan, peaks):
                 nat.set_pdl(old)
         return f
 
+    def only_igemm():
+        old = nat.set_pdl(plan.pdl)
+        try:
+            for op, ig in zip(plan.ops, is_ig):
+                if ig:
+                    op()
+        finally:
+            nat.set_pdl(old)
+
     full_ms = _graph_ms(runner(False))
     rest_ms = _graph_ms(runner(True))
     ig_ms = max(full_ms - rest_ms, 1e-6)
+    # cross-check: the 148 igemm launches alone, back to back in plan order, in one graph (operands = what the full
+    # run left in the buffers); no subtraction, but no neighbours to overlap with either
+    only_ms = _graph_ms(only_igemm)
     n = sum(is_ig)
     achieved = flops / (ig_ms / 1e3) / 1e12
     # dram bytes per launch of this kernel from the committed ncu --set full capture (tools/make_traffic_json.py)
@@ -355,6 +367,9 @@ def kernel_roofline(plan, peaks):
             "traffic": traffic, "traffic_source": traffic_src, "launches": n, "algorithmic_gflop_per_launch": round(flops / 1e9 / max(n, 1), 2),
             "algorithmic_gflop_per_forward": round(flops / 1e9, 1), "avg_launch_us": round(ig_ms * 1e3 / max(n, 1), 2),
             "share_of_unet_forward": round(ig_ms / full_ms, 3), "unet_forward_ms_graph": round(full_ms, 3),
+            "frac_of_sustained_peak": round(achieved / peaks["sustained"], 4),
+            "igemm_only_graph": {"ms": round(only_ms, 3), "achieved": round(flops / (only_ms / 1e3) / 1e12, 2),
+                                 "frac": round(flops / (only_ms / 1e3) / 1e12 / peaks["burst"], 4)},
             "method": "in-graph: CUDA-event time of the UNet-forward graph minus the same graph without its "
                       "igemm launches (batch as benchmarked)"}
 

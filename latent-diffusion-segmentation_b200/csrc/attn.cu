@@ -16,8 +16,8 @@
 // with its own softmax warpgroup; while one warpgroup exponentiates S_j the tensor core computes the
 // other tile's S and P.V (ping-pong), and K/V tiles are loaded once for both.
 //
-// CTA = 384 threads:  warps 0..3 softmax/correction of query tile 0 | warps 4..7 of query tile 1 |
-//                     warps 8 / 9 MMA issuer of query tile 0 / 1 (8 allocates TMEM) | warp 10 TMA producer | warp 11 idle
+// CTA = 8 HS softmax warps (query tile 0, then 1; per tile the column halves, per half the four TMEM lane quadrants)
+//       + MMA issuer of tile 0 (allocates TMEM) | MMA issuer of tile 1 | TMA producer | idle warp      (see AttnRoles)
 // TMEM: S0 at [0,BKV), S1 at [BKV,2BKV), O0 at [2BKV, 2BKV+dk), O1 at [2BKV+dk, 2BKV+2dk), then P0, P1 (BKV/2
 // columns each: two bf16 per 32-bit cell, K-contiguous -- the layout tcgen05.mma expects of a K-major A operand in
 // tensor memory)  (<= 512 columns: 480 / 352 / 512 at d = 40 / 80 / 160).
@@ -34,18 +34,30 @@
 
 namespace ldm {
 
-constexpr int kAttnThreads = 384;
-// Warp roles: two softmax warpgroups (query tile 0 / 1), and a control warpgroup with ONE MMA-issuing warp PER query
-// tile, the TMA producer and an idle warp.  Per tile the order of the tensor-core work is fixed -- S(j+1) becomes
-// issuable (S(j) copied to registers) before P(j) is ready -- so each issuer runs a plain blocking sequence of
-// mbarrier waits.  A single issuer serving both tiles had to poll four barriers in an event loop; a polling round
-// took ~700 cycles and with every stage of the pipeline removed but the hand-shakes the kernel still ran at half
-// its full time (tools/attn_timing.py, ablation builds).
-// Three warpgroups also let the register file be re-split (setmaxnreg works on aligned groups of four warps): the
-// control warpgroup gives up all but 40 registers per thread, the softmax warpgroups grow from 168 to 232 -- a thread
-// holds a whole 128-column score row plus the packed P.
-constexpr int kSoftmaxWarp0 = 0, kCtrlWarp0 = 8, kMmaWarp0 = 8, kTmaWarp = 10;
-constexpr int kCtrlRegs = 40, kSoftmaxRegs = 232;
+// Warp roles: softmax warpgroups first, then a control warpgroup with ONE MMA-issuing warp PER query tile, the TMA
+// producer and an idle warp.  Per tile the order of the tensor-core work is fixed -- S(j+1) becomes issuable (S(j)
+// copied to registers) before P(j) is ready -- so each issuer runs a plain blocking sequence of mbarrier waits.  A
+// single issuer serving both tiles had to poll four barriers in an event loop; with every stage of the pipeline removed
+// but the hand-shakes the kernel still ran at half its full time (tools/attn_timing.py, ablation builds).
+//
+// HS = column halves per score row.  HS = 1: a thread owns a whole row of its query tile (two softmax warpgroups, 232
+// registers each after setmaxnreg).  HS = 2 (the 128-key tiles of d = 40): a row is shared by two threads of two
+// different warps, 64 columns each -- four softmax warps per scheduler instead of two.  The softmax is a chain of
+// in-order latencies (TMEM load -> row maximum -> scale -> MUFU -> sum -> pack -> TMEM store, ~600 instructions per
+// 128-key tile in ~2 800 cycles with two warps per scheduler); what it lacked was independent warps to issue from,
+// not pipe throughput.  The two halves agree on the running maximum through shared memory (one named barrier of 64
+// threads per iteration); each keeps its own partial row sum.
+template <int HS>
+struct AttnRoles {
+  static constexpr int kSoftmaxWarps = 8 * HS;
+  static constexpr int kCtrlWarp0 = 8 * HS;        // MMA issuers kCtrlWarp0 / +1 (+0 allocates TMEM), TMA producer +2, idle +3
+  static constexpr int kThreads = (8 * HS + 4) * 32;
+  // setmaxnreg (aligned groups of four warps): the control warpgroup gives its registers to the softmax warps
+  // (the pool a warp can grow from holds only what other warps of the CTA released: 384 threads start at 168
+  // registers, 128 x (168 - 40) = 256 x (232 - 168); 640 threads start at 96, 128 x (96 - 32) = 512 x (112 - 96))
+  static constexpr int kCtrlRegs = HS == 2 ? 32 : 40;
+  static constexpr int kSoftmaxRegs = HS == 2 ? 112 : 232;
+};
 
 template <int D>
 struct AttnCfg {
@@ -58,7 +70,11 @@ struct AttnCfg {
   // K/V ring depth: a K/V tile is only reloaded after both P.V products that read it have completed, and the
   // next S product needs the tile after that one, so two stages expose the whole TMA latency every iteration
   static constexpr int kKVStages = (D <= 80) ? 4 : 2;
-  static constexpr int kSmemBytes = 2 * kQBytes + kKVStages * 2 * kKBytes + 2 * kPBytes + 24 * 8 + 1024;
+  // + barriers, + 6 KB of row-maximum / row-sum exchange between the column halves of a row (HS = 2)
+  // (the P staging only when P goes through shared memory)
+  static constexpr int smem_bytes(bool p_in_tmem) {
+    return 2 * kQBytes + kKVStages * 2 * kKBytes + (p_in_tmem ? 0 : 2 * kPBytes) + 24 * 8 + 6144 + 64 + 1024;
+  }
   static constexpr int kTmemCols = 512;
   static constexpr int kOCol = 2 * BKV;   // S0 at [0,BKV), S1 at [BKV,2BKV), then O0, O1 (dk columns each)
   static constexpr int kPCol = kOCol + 2 * kDK;   // P0, P1: BKV/2 columns each (bf16 pairs)
@@ -152,9 +168,14 @@ __device__ unsigned int g_attn_timing[32];
 
 // PM: share of the exponentials evaluated on the FMA pipe (0 = none, 1 = half, 2 = a quarter)
 // PT: P goes to tensor memory (A operand from TMEM) instead of shared memory
-template <int D, int PM, bool PT>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
+template <int D, int PM, bool PT, int HS>
+__global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<D>;
+  using Roles = AttnRoles<HS>;
+  static_assert(HS == 1 || (PT && Cfg::BKV % 128 == 0), "column halves: P in tensor memory, 128-key tiles");
+  constexpr int kSoftmaxWarp0 = 0, kCtrlWarp0 = Roles::kCtrlWarp0, kMmaWarp0 = Roles::kCtrlWarp0,
+                kTmaWarp = Roles::kCtrlWarp0 + 2;
+  constexpr int kCtrlRegs = Roles::kCtrlRegs, kSoftmaxRegs = Roles::kSoftmaxRegs;
   constexpr int BKV = Cfg::BKV;
   constexpr int kPanels = Cfg::kPanels;
   constexpr int kDK = Cfg::kDK;
@@ -167,7 +188,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   uint8_t* sm_k = sm_q + 2 * Cfg::kQBytes;           // [2 stages][K]
   uint8_t* sm_v = sm_k + KS * Cfg::kKBytes;          // [stages][V]
   uint8_t* sm_p = sm_v + KS * Cfg::kKBytes;          // [2 query tiles][P]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 2 * Cfg::kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + (PT ? 0 : 2 * Cfg::kPBytes));
   uint64_t* q_full = bars + 0;
   uint64_t* s_full = bars + 1;    // [2] per query tile
   uint64_t* p_full = bars + 3;    // [2]
@@ -176,6 +197,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   uint64_t* kv_full = bars + 9;   // [stages]
   uint64_t* kv_empty = bars + 9 + KS;  // [stages]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9 + 2 * KS);
+  // HS = 2: [iteration parity][tile][half][row] row maxima, then [tile][half][row] row sums
+  float* xch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem) + 4 + 15) & ~static_cast<uintptr_t>(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,9 +225,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 128 * HS);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 128);
+      mbar_init(&s_free[i], 128 * HS);
     }
     fence_mbar_init();
   }
@@ -323,15 +346,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 #endif
     }
     __syncwarp();
-  } else if (warp >= kSoftmaxWarp0 && warp < kSoftmaxWarp0 + 8) {
+  } else if (warp >= kSoftmaxWarp0 && warp < kSoftmaxWarp0 + 8 * HS) {
     // ---------------------------------------------------------------- softmax / correction
     setmaxnreg_inc<kSoftmaxRegs>();
-    const int t = (warp - kSoftmaxWarp0) >> 2;  // query tile of this warpgroup
-    const int q = warp & 3;         // TMEM lane quadrant
+    constexpr int NC = BKV / HS;                      // score columns per thread
+    const int t = (warp - kSoftmaxWarp0) / (4 * HS);  // query tile
+    const int h = ((warp - kSoftmaxWarp0) >> 2) % HS; // column half of the row
+    const int q = warp & 3;                           // TMEM lane quadrant
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_off + t * BKV;
+    const uint32_t s_addr = tmem_base + lane_off + t * BKV + h * NC;
     const uint32_t o_addr = tmem_base + lane_off + Cfg::kOCol + t * kDK;
+    // the O columns this thread corrects / writes out: its half of the (padded) head dimension, in groups of 8
+    constexpr int kOGroups = kDK / 8;
+    const int c_lo = 8 * (h * kOGroups / HS), c_hi = 8 * ((h + 1) * kOGroups / HS);
+    const int xbar = 2 + t * 4 + q;                   // named barrier shared by the two threads' warps (HS = 2)
     const uint32_t my_p_u32 = smem_u32(sm_p + t * Cfg::kPBytes);
     const float scale = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
@@ -343,25 +372,25 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       tc_fence_after();
       ATT_TICK(0);   // wait for S
       // the whole score row goes to registers in one pass; S_t in TMEM is then free for the next product
-      uint32_t sr[BKV];
+      uint32_t sr[NC];
       if (!(dbg & 2) || j == 0) {
 #pragma unroll
-        for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(s_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
+        for (int c = 0; c < NC; c += 32) tmem_ld_32x32(s_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&sr[c]));
         tmem_wait_ld();
       }
       tc_fence_before();
       mbar_arrive(&s_free[t]);
       ATT_TICK(1);   // S row -> registers
-      const int kv_valid = p.ntok_kv - j * BKV;  // columns < kv_valid are real tokens
-      if (kv_valid < BKV) {
+      const int kv_valid = p.ntok_kv - j * BKV - h * NC;  // my columns < kv_valid are real tokens
+      if (kv_valid < NC) {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i)
+        for (int i = 0; i < NC; ++i)
           if (i >= kv_valid) sr[i] = 0xff800000u;  // -inf
       }
       // row maximum (3-input max, four independent chains)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < BKV; i += 8) {
+      for (int i = 0; i < NC; i += 8) {
         mx0 = max3f(mx0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
         mx1 = max3f(mx1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
         mx2 = max3f(mx2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
@@ -369,6 +398,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       }
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;
       if (dbg & 32) mx = __uint_as_float(sr[0]) * scale;
+      if constexpr (HS == 2) {
+        // both halves of the row must take the same decision about the running maximum.  Slots alternate with the
+        // iteration parity: a slot is rewritten two iterations later, after a barrier both threads have passed since
+        // the partner read it
+        float* mine = xch + (((j & 1) * 2 + t) * 2 + h) * 128 + row;
+        *mine = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(xbar) : "memory");
+        mx = fmaxf(mx, mine[(h ? -128 : 128)]);
+      }
       // lazy rescaling: the running maximum only moves when the new one exceeds it by more than 2^8, so P
       // stays <= 256 (exact in bf16's range, fp32 accumulation) and O is corrected a handful of times per row
       float alpha = 1.f;
@@ -380,9 +418,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       ATT_TICK(2);   // row maximum
       // p = exp2(s*scale - m): packed FFMA2, one MUFU each, packed FADD2 row sums, bf16 pairs
       float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
-      uint32_t pk[BKV / 2];
+      uint32_t pk[NC / 2];
 #pragma unroll
-      for (int i = 0; i < BKV; i += 4) {
+      for (int i = 0; i < NC; i += 4) {
         float2 a = fma2(make_float2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), scale, negm);
         float2 b = fma2(make_float2(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])), scale, negm);
         if (!(dbg & 1)) {
@@ -409,9 +447,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       if (dbg & 16) {
       } else if constexpr (PT) {
         // thread = query row = TMEM lane: its BKV/2 packed pairs go to consecutive columns of P_t
-        const uint32_t p_addr = tmem_base + lane_off + Cfg::kPCol + t * (BKV / 2);
+        const uint32_t p_addr = tmem_base + lane_off + Cfg::kPCol + t * (BKV / 2) + h * (NC / 2);
 #pragma unroll
-        for (int c = 0; c < BKV / 2; c += 32) tmem_st_32x32(p_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&pk[c]));
+        for (int c = 0; c < NC / 2; c += 32) tmem_st_32x32(p_addr + c, *reinterpret_cast<uint32_t(*)[32]>(&pk[c]));
       } else {
 #pragma unroll
         for (int c8 = 0; c8 < BKV / 8; ++c8) {
@@ -424,14 +462,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       // correction: O *= alpha (skipped warp-uniformly when no row of this warp moved its max)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
-        for (int c = 0; c < kDK; c += 16) {
-          uint32_t r[16];
-          tmem_ld_32x16(o_addr + c, r);
+        for (int c = c_lo; c < c_hi; c += 8) {
+          uint32_t r[8];
+          tmem_ld_32x8(o_addr + c, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x8(o_addr + c, *reinterpret_cast<uint32_t(*)[8]>(&r[0]));
-          tmem_st_32x8(o_addr + c + 8, *reinterpret_cast<uint32_t(*)[8]>(&r[8]));
+          for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x8(o_addr + c, r);
         }
       }
       if constexpr (PT) tmem_wait_st();        // P (and the corrected O) are in tensor memory before the MMA reads them
@@ -444,17 +481,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       ATT_TICK(6);   // P store (+ correction)
     }
 #ifdef LDMSEG_ATTN_TIMING
-    if (blockIdx.x == 0 && lane == 0 && q == 0)
+    if (blockIdx.x == 0 && lane == 0 && q == 0 && h == 0)
       for (int i = 0; i < 8; ++i) g_attn_timing[t * 8 + i] = tacc[i];
 #endif
     // ---------------------------------------------------------------- final normalisation
     mbar_wait(&pv_done[t], static_cast<uint32_t>(T - 1) & 1);
     tc_fence_after();
+    if constexpr (HS == 2) {   // the row sum is the two halves' partial sums (same scaling: same running maximum)
+      float* mine = xch + 4 * 128 * 2 + (t * 2 + h) * 128 + row;
+      *mine = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(xbar) : "memory");
+      l_run += mine[(h ? -128 : 128)];
+    }
     const float inv_l = 1.f / l_run;
     const int tok = q0 + t * 128 + row;
     __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * p.ntok + tok) * (p.heads * D) + head * D;
 #pragma unroll 1
-    for (int c = 0; c < kDK; c += 8) {
+    for (int c = c_lo; c < c_hi; c += 8) {
       uint32_t r[8];
       tmem_ld_32x8(o_addr + c, r);
       tmem_wait_ld();
@@ -539,7 +582,7 @@ __global__ void attn_simple_kernel(const __nv_bfloat16* __restrict__ qkv, int nb
 
 // q_src: bf16 [nb*ntok, q_which_n * heads * D] (column block 0 = Q); kv_src: bf16 [nb*ntok_kv, kv_which_n * heads * D]
 // with K / V in column blocks k_which / v_which.  Self-attention: q_src = kv_src = the fused QKV, (3, 1, 2).
-template <int D, int PM, bool PT>
+template <int D, int PM, bool PT, int HS>
 static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which,
                           int v_which, int nb, int ntok, int ntok_kv, int heads, void* out, cudaStream_t st) {
   using Cfg = AttnCfg<D>;
@@ -566,12 +609,12 @@ static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, 
   kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
+    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM, PT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::smem_bytes(PT)));
     configured = true;
   }
   const int grid = nb * heads * ((ntok + 255) / 256);
-  launch_kernel(attn_kernel<D, PM, PT>, dim3(grid), dim3(kAttnThreads), Cfg::kSmemBytes, st, kp);
+  launch_kernel(attn_kernel<D, PM, PT, HS>, dim3(grid), dim3(AttnRoles<HS>::kThreads), Cfg::smem_bytes(PT), st, kp);
   return check_launch("attn_kernel");
 }
 
@@ -588,19 +631,33 @@ static int launch_attn(const void* q_src, int q_which_n, const void* kv_src, int
     const char* e = getenv("LDMSEG_ATTN_PTMEM");
     pt = e ? atoi(e) : 1;
   }
-#define LDM_ATTN_CASE(PMV, PTV) \
-  return launch_attn_pm<D, PMV, PTV>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st)
+  static int hs = -1;   // LDMSEG_ATTN_HALVES=1: one thread per score row also for the 128-key tiles (A/B timing)
+  if (hs < 0) {
+    const char* e = getenv("LDMSEG_ATTN_HALVES");
+    hs = e ? atoi(e) : 2;
+  }
+#define LDM_ATTN_CASE(PMV, PTV, HSV) \
+  return launch_attn_pm<D, PMV, PTV, HSV>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st)
+  if constexpr (AttnCfg<D>::BKV == 128) {
+    if (pt && hs == 2) {
+      switch (pm) {
+        case 0: LDM_ATTN_CASE(0, true, 2);
+        case 1: LDM_ATTN_CASE(1, true, 2);
+        default: LDM_ATTN_CASE(2, true, 2);
+      }
+    }
+  }
   if (pt) {
     switch (pm) {
-      case 0: LDM_ATTN_CASE(0, true);
-      case 1: LDM_ATTN_CASE(1, true);
-      default: LDM_ATTN_CASE(2, true);
+      case 0: LDM_ATTN_CASE(0, true, 1);
+      case 1: LDM_ATTN_CASE(1, true, 1);
+      default: LDM_ATTN_CASE(2, true, 1);
     }
   }
   switch (pm) {
-    case 0: LDM_ATTN_CASE(0, false);
-    case 1: LDM_ATTN_CASE(1, false);
-    default: LDM_ATTN_CASE(2, false);
+    case 0: LDM_ATTN_CASE(0, false, 1);
+    case 1: LDM_ATTN_CASE(1, false, 1);
+    default: LDM_ATTN_CASE(2, false, 1);
   }
 #undef LDM_ATTN_CASE
 }
