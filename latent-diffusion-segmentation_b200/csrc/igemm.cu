@@ -1088,15 +1088,25 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         // until all splits of this tile have arrived.  Peers are CTAs of the same persistent grid in
         // the same round, so they are running or about to be scheduled (1 CTA per SM, grid <= #SMs).
         if (p.debug & 2) continue;
+        // the operands of the final pass that do not depend on the peers (bias, per-image bias, residual rows of the
+        // units this split will finish) start their trip from L2 now, under the publish / wait below
+        csplit_prefetch_epilogue<BN>(ea, p.split_k, split, m_tile * BM, n0, warp - 2, lane);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-          int seen;
-          asm volatile("atom.release.gpu.global.add.s32 %0, [%1], 1;" : "=r"(seen) : "l"(p.counters + tile) : "memory");
+          // One self-re-arming counter per tile, counting modulo 2 S with wrapping increments: S arrivals (release),
+          // then S departures.  A split spins until the count is >= S; it departs only after that, so the count wraps
+          // to 0 -- the state the next launch expects -- only once nobody can still be spinning.  The departure is a
+          // fire-and-forget reduction: no thread waits for an atomic's round trip before the CTA retires (the earlier
+          // scheme -- a second counter, atom.acq_rel, the last split resets both -- held every CTA for that trip).
+          const unsigned wrap = 2u * static_cast<unsigned>(p.split_k) - 1u;
+          unsigned seen;
+          asm volatile("red.release.gpu.global.inc.u32 [%0], %1;" ::"l"(p.counters + tile), "r"(wrap) : "memory");
           uint32_t spins = 0;
           do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
             if (++spins > (1u << 26)) __trap();
-          } while (seen < p.split_k);
+          } while (seen < static_cast<unsigned>(p.split_k));
+          asm volatile("red.relaxed.gpu.global.inc.u32 [%0], %1;" ::"l"(p.counters + tile), "r"(wrap) : "memory");
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (!(p.debug & 1)) {
@@ -1107,17 +1117,6 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
                                          reinterpret_cast<float*>(smem_a));
           else
             epilogue_warp<BN, GEGLU, EPI_FINAL, NH>(ea, 0, ws_tile, split, m_base, n0, q, half, lane, ln_rs);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-          // the last CTA to finish its share re-arms both counters for the next launch
-          int* done = p.counters + 4096 + tile;
-          int old;
-          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(done) : "memory");
-          if (old == p.split_k - 1) {
-            p.counters[tile] = 0;
-            *done = 0;
-          }
         }
       }
     }
