@@ -990,6 +990,28 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       if (ea.ln_rowstats != nullptr && m_base + lane < ea.M)
         ln_rs = __ldcg(reinterpret_cast<const float2*>(ea.ln_rowstats) + m_base + lane);
       if constexpr (CSPLIT) csplit_prefetch_epilogue<BN>(ea, p.split_k, split, m_tile * BM, n0, warp - 2, lane);
+      if constexpr (!SPLIT) {
+        // First tile of this CTA: the epilogue warps have nothing to do until the MMAs finish, and what follows is a
+        // chain of short dependent steps per 32-column chunk (TMEM load -> bias -> residual -> store).  Start the
+        // residual rows and the bias vectors of the tile on their way to L1 now.  (Later tiles of a persistent CTA
+        // overlap their epilogue with the next tile's MMAs anyway.)
+        if (it == 0 && !(p.debug & 512)) {
+          const int m = m_base + lane;
+          const int ncols = min(BN, ea.N - n0);
+          if (ea.residual != nullptr && m < ea.M) {
+            const int esz = ea.res_f32 ? 4 : 2;
+            const uint8_t* rp = reinterpret_cast<const uint8_t*>(ea.residual) +
+                                (static_cast<size_t>(m) * ea.res_ld + n0) * esz;
+            for (int off = half * 128; off < ncols * esz; off += NH * 128) prefetch_l1(rp + off);
+          }
+          if (q == 0 && lane < (ncols * 4 + 127) / 128 && (lane % NH) == half) {
+            if (ea.bias != nullptr) prefetch_l1(ea.bias + n0 + lane * 32);
+            if (ea.rowbias != nullptr && m_base < ea.M)
+              prefetch_l1(ea.rowbias + static_cast<size_t>(m_base / ea.HW) * ea.rowbias_ld + n0 + lane * 32);
+            if (ea.ln_colsum != nullptr) prefetch_l1(ea.ln_colsum + n0 + lane * 32);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
