@@ -47,11 +47,16 @@ namespace ldm {
 // 128-key tile in ~2 800 cycles with two warps per scheduler); what it lacked was independent warps to issue from,
 // not pipe throughput.  The two halves agree on the running maximum through shared memory (one named barrier of 64
 // threads per iteration); each keeps its own partial row sum.
-template <int HS>
+// NT = query tiles per CTA.  NT = 2 shares every K/V tile between two query tiles and lets the tensor core work for one
+// tile while the other exponentiates; NT = 1 halves the work per CTA and doubles the CTA count -- for the launches that
+// cannot fill the machine otherwise (batch 1: 1024 tokens = 32 CTAs of two tiles, 256 tokens = 8), where the kernel's
+// time is the length of one CTA's serial K/V loop.
+template <int HS, int NT = 2>
 struct AttnRoles {
-  static constexpr int kSoftmaxWarps = 8 * HS;
-  static constexpr int kCtrlWarp0 = 8 * HS;        // MMA issuers kCtrlWarp0 / +1 (+0 allocates TMEM), TMA producer +2, idle +3
-  static constexpr int kThreads = (8 * HS + 4) * 32;
+  static constexpr int kSoftmaxWarps = 4 * HS * NT;
+  static constexpr int kCtrlWarp0 = 4 * HS * NT;   // MMA issuers kCtrlWarp0 (+1 for the second tile; +0 allocates TMEM), TMA producer +2, idle
+  static constexpr int kThreads = (4 * HS * NT + 4) * 32;
+  static constexpr bool kResplit = NT == 2;        // NT = 1: 256 threads, up to 255 registers each without setmaxnreg
   // setmaxnreg (aligned groups of four warps): the control warpgroup gives its registers to the softmax warps
   // (the pool a warp can grow from holds only what other warps of the CTA released: 384 threads start at 168
   // registers, 128 x (168 - 40) = 256 x (232 - 168); 640 threads start at 96, 128 x (96 - 32) = 512 x (112 - 96))
@@ -168,11 +173,12 @@ __device__ unsigned int g_attn_timing[32];
 
 // PM: share of the exponentials evaluated on the FMA pipe (0 = none, 1 = half, 2 = a quarter)
 // PT: P goes to tensor memory (A operand from TMEM) instead of shared memory
-template <int D, int PM, bool PT, int HS>
-__global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
+template <int D, int PM, bool PT, int HS, int NT>
+__global__ void __launch_bounds__(AttnRoles<HS, NT>::kThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<D>;
-  using Roles = AttnRoles<HS>;
+  using Roles = AttnRoles<HS, NT>;
   static_assert(HS == 1 || (PT && Cfg::BKV % 128 == 0), "column halves: P in tensor memory, 128-key tiles");
+  static_assert(NT == 2 || (NT == 1 && HS == 1 && PT), "one query tile per CTA: one thread per row, P in tensor memory");
   constexpr int kSoftmaxWarp0 = 0, kCtrlWarp0 = Roles::kCtrlWarp0, kMmaWarp0 = Roles::kCtrlWarp0,
                 kTmaWarp = Roles::kCtrlWarp0 + 2;
   constexpr int kCtrlRegs = Roles::kCtrlRegs, kSoftmaxRegs = Roles::kSoftmaxRegs;
@@ -208,11 +214,11 @@ __global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const 
   constexpr int dbg = 0;
 #endif
 
-  const int q_blocks = (p.ntok + 255) / 256;
+  const int q_blocks = (p.ntok + 128 * NT - 1) / (128 * NT);
   const int qb = blockIdx.x % q_blocks;
   const int head = (blockIdx.x / q_blocks) % p.heads;
   const int b = blockIdx.x / (q_blocks * p.heads);
-  const int q0 = qb * 256;
+  const int q0 = qb * 128 * NT;
   const int T = (p.ntok_kv + BKV - 1) / BKV;
 
   if (warp == kTmaWarp && lane == 0) {
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const 
     mbar_init(q_full, 1);
     for (int i = 0; i < KS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);   // both tiles' issuers release a stage
+      mbar_init(&kv_empty[i], NT);   // every tile's issuer releases a stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -244,11 +250,13 @@ __global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const 
   pdl_trigger();
   pdl_wait();  // the prologue above overlapped the previous kernel; inputs are read from here on
 
-  if (warp >= kCtrlWarp0 && warp < kCtrlWarp0 + 4) setmaxnreg_dec<kCtrlRegs>();
+  if constexpr (Roles::kResplit) {
+    if (warp >= kCtrlWarp0 && warp < kCtrlWarp0 + 4) setmaxnreg_dec<kCtrlRegs>();
+  }
   if (warp == kTmaWarp) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * Cfg::kQBytes);
-      for (int t = 0; t < 2; ++t)
+      mbar_expect_tx(q_full, NT * Cfg::kQBytes);
+      for (int t = 0; t < NT; ++t)
         for (int pn = 0; pn < kPanels; ++pn)
           tma_load_5d(sm_q + t * Cfg::kQBytes + pn * 128 * 128, &p.map_q, q_full, pn * 64, head, 0,
                       q0 + t * 128, b);
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const 
       }
     }
     __syncwarp();
-  } else if (warp == kMmaWarp0 || warp == kMmaWarp0 + 1) {
+  } else if (warp >= kMmaWarp0 && warp < kMmaWarp0 + NT) {
     if (elect_one()) {
       const int t = warp - kMmaWarp0;   // the query tile this issuer serves
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
@@ -346,9 +354,9 @@ __global__ void __launch_bounds__(AttnRoles<HS>::kThreads, 1) attn_kernel(const 
 #endif
     }
     __syncwarp();
-  } else if (warp >= kSoftmaxWarp0 && warp < kSoftmaxWarp0 + 8 * HS) {
+  } else if (warp >= kSoftmaxWarp0 && warp < kSoftmaxWarp0 + Roles::kSoftmaxWarps) {
     // ---------------------------------------------------------------- softmax / correction
-    setmaxnreg_inc<kSoftmaxRegs>();
+    if constexpr (Roles::kResplit) setmaxnreg_inc<kSoftmaxRegs>();
     constexpr int NC = BKV / HS;                      // score columns per thread
     const int t = (warp - kSoftmaxWarp0) / (4 * HS);  // query tile
     const int h = ((warp - kSoftmaxWarp0) >> 2) % HS; // column half of the row
@@ -582,7 +590,7 @@ __global__ void attn_simple_kernel(const __nv_bfloat16* __restrict__ qkv, int nb
 
 // q_src: bf16 [nb*ntok, q_which_n * heads * D] (column block 0 = Q); kv_src: bf16 [nb*ntok_kv, kv_which_n * heads * D]
 // with K / V in column blocks k_which / v_which.  Self-attention: q_src = kv_src = the fused QKV, (3, 1, 2).
-template <int D, int PM, bool PT, int HS>
+template <int D, int PM, bool PT, int HS, int NT>
 static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, int kv_which_n, int k_which,
                           int v_which, int nb, int ntok, int ntok_kv, int heads, void* out, cudaStream_t st) {
   using Cfg = AttnCfg<D>;
@@ -609,12 +617,13 @@ static int launch_attn_pm(const void* q_src, int q_which_n, const void* kv_src, 
   kp.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
   static bool configured = false;
   if (!configured) {
-    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM, PT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDM_CUDA(cudaFuncSetAttribute(attn_kernel<D, PM, PT, HS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::smem_bytes(PT)));
     configured = true;
   }
-  const int grid = nb * heads * ((ntok + 255) / 256);
-  launch_kernel(attn_kernel<D, PM, PT, HS>, dim3(grid), dim3(AttnRoles<HS>::kThreads), Cfg::smem_bytes(PT), st, kp);
+  const int grid = nb * heads * ((ntok + 128 * NT - 1) / (128 * NT));
+  launch_kernel(attn_kernel<D, PM, PT, HS, NT>, dim3(grid), dim3(AttnRoles<HS, NT>::kThreads), Cfg::smem_bytes(PT), st,
+                kp);
   return check_launch("attn_kernel");
 }
 
@@ -636,28 +645,42 @@ static int launch_attn(const void* q_src, int q_which_n, const void* kv_src, int
     const char* e = getenv("LDMSEG_ATTN_HALVES");
     hs = e ? atoi(e) : 2;
   }
-#define LDM_ATTN_CASE(PMV, PTV, HSV) \
-  return launch_attn_pm<D, PMV, PTV, HSV>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st)
+  static int nt1 = -1;  // LDMSEG_ATTN_SINGLE=0: always two query tiles per CTA (A/B timing)
+  if (nt1 < 0) {
+    const char* e = getenv("LDMSEG_ATTN_SINGLE");
+    nt1 = e ? atoi(e) : 1;
+  }
+#define LDM_ATTN_CASE(PMV, PTV, HSV, NTV) \
+  return launch_attn_pm<D, PMV, PTV, HSV, NTV>(q_src, q_which_n, kv_src, kv_which_n, k_which, v_which, nb, ntok, ntok_kv, heads, out, st)
   if constexpr (AttnCfg<D>::BKV == 128) {
     if (pt && hs == 2) {
       switch (pm) {
-        case 0: LDM_ATTN_CASE(0, true, 2);
-        case 1: LDM_ATTN_CASE(1, true, 2);
-        default: LDM_ATTN_CASE(2, true, 2);
+        case 0: LDM_ATTN_CASE(0, true, 2, 2);
+        case 1: LDM_ATTN_CASE(1, true, 2, 2);
+        default: LDM_ATTN_CASE(2, true, 2, 2);
+      }
+    }
+  } else {
+    // a launch of two-tile CTAs that leaves most SMs idle: one tile per CTA, twice the CTAs, half the serial loop
+    if (pt && nt1 && ntok > 128 && static_cast<long long>(nb) * heads * ((ntok + 255) / 256) <= num_sms() / 2) {
+      switch (pm) {
+        case 0: LDM_ATTN_CASE(0, true, 1, 1);
+        case 1: LDM_ATTN_CASE(1, true, 1, 1);
+        default: LDM_ATTN_CASE(2, true, 1, 1);
       }
     }
   }
   if (pt) {
     switch (pm) {
-      case 0: LDM_ATTN_CASE(0, true, 1);
-      case 1: LDM_ATTN_CASE(1, true, 1);
-      default: LDM_ATTN_CASE(2, true, 1);
+      case 0: LDM_ATTN_CASE(0, true, 1, 2);
+      case 1: LDM_ATTN_CASE(1, true, 1, 2);
+      default: LDM_ATTN_CASE(2, true, 1, 2);
     }
   }
   switch (pm) {
-    case 0: LDM_ATTN_CASE(0, false, 1);
-    case 1: LDM_ATTN_CASE(1, false, 1);
-    default: LDM_ATTN_CASE(2, false, 1);
+    case 0: LDM_ATTN_CASE(0, false, 1, 2);
+    case 1: LDM_ATTN_CASE(1, false, 1, 2);
+    default: LDM_ATTN_CASE(2, false, 1, 2);
   }
 #undef LDM_ATTN_CASE
 }
