@@ -49,7 +49,8 @@ def _tuned_table() -> Dict[str, list]:
     """Measured (block_n, split_k, pair) per (M, N, k-blocks) from tools/tune_tiling.py; empty if absent."""
     global _TUNED
     if _TUNED is None:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_b200.json")
+        path = os.environ.get("LDMSEG_TUNED_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                   "tuned_b200.json")
         try:
             with open(path) as f:
                 _TUNED = json.load(f).get("entries", {})
