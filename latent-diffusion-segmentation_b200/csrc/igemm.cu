@@ -82,8 +82,11 @@ struct alignas(64) IgemmKParams {
   int tail_tiles;
   int tail_slots;      // workspace slots (partial tiles) per tail tile
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
-  int debug;          // development only: bit0 skip final reduce, bit1 skip sync, bit2 skip partial store,
-                      // bit3 / bit4 leave the A / B loads out after a work item's first k-block, bit5 drop the epilogue
+  int debug;          // development only (ldmseg_set_debug; timing experiments, results are garbage):
+                      // bit0 split-K without the final reduce, bit1 without publish / wait / reduce, bit2 without the
+                      // partial store; bit3 / bit4 leave the A / B loads out after a work item's first k-block; bit5 drop
+                      // the epilogue; bit6 launch the workspace split-K as clusters; bit7 no fused GroupNorm statistics
+                      // (valid off the power cap only); bit9 no first-tile epilogue prefetch
 };
 
 // PAIR: two CTAs of a cluster work as one 256 x BN tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
