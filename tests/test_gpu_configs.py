@@ -388,3 +388,26 @@ def test_training_step_forward_reuse(dev, unets):
     torch.testing.assert_close(an.cpu(), r_noisy, rtol=1e-6, atol=1e-6)
     rn = sch.remove_noise(an, noise.to(dev), t.to(dev))
     torch.testing.assert_close(rn.cpu(), lat, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ configs[2] share
+def test_batch_independence_at_config3_size(dev, unets):
+    """A size-independent property at BASELINE configs[2]'s per-GPU share (batch 8, 64x64 latent): every image's
+    chain is independent of its batch mates, although the batch-8 plan uses other kernels than the
+    batch-1 plan (CTA pairs, the stream-K tail, two-tile attention CTAs against split-K, single-tile CTAs).  Ten
+    steps of the fused sampler on 8 images against the same images one at a time."""
+    from ldmseg.engine.sampler import B200Sampler
+    from ldmseg.schedulers import DDIMNoiseScheduler
+    from oracle.make_golden import SCHED_KW
+    _, unet = unets
+    sampler = B200Sampler(unet, DDIMNoiseScheduler(**SCHED_KW))
+    g = torch.Generator().manual_seed(11)
+    rgb = (torch.randn(8, 4, 64, 64, generator=g) * 0.18215 * 4).to(dev)
+    noise = torch.randn(8, 4, 64, 64, generator=g)
+    z8 = sampler.sample(rgb, 10, seed=0, noise=noise).clone()
+    errs = []
+    for i in (0, 3, 7):
+        z1 = sampler.sample(rgb[i:i + 1].contiguous(), 10, seed=0, noise=noise[i:i + 1].contiguous())
+        errs.append(rel_l2(z8[i:i + 1], z1))
+    record("batch_independence_b8_vs_b1_10steps", rel_l2=errs)
+    assert max(errs) < 5e-3, errs
