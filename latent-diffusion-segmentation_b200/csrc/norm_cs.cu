@@ -7,6 +7,7 @@
 // Replaces nn.GroupNorm + nn.SiLU of diffusers ResnetBlock2D.norm1/norm2, Transformer2DModel.norm and
 // UNet.conv_norm_out (/root/reference/ldmseg/models/unet.py:428-430).
 #include "common.h"
+#include <cstdlib>
 #include <type_traits>
 #include "ptx.cuh"
 #include "../../include/ldmseg_b200.h"
@@ -198,7 +199,14 @@ static int gn_apply_cs_launch(const void* src0, int c0, const float* chan_stats0
   const int threads = (C8 * lanes + 31) / 32 * 32;
   // enough CTAs to fill the machine twice over, but at least 4 pixels per lane per CTA
   int chunks = (2 * num_sms() + nb - 1) / nb;
-  int cmax = (hw + 4 * lanes - 1) / (4 * lanes);
+  // (small images: one pixel per lane, so that the launch still spreads over tens of SMs -- LDMSEG_GN_MINPX overrides)
+  static int min_px_env = -1;
+  if (min_px_env < 0) {
+    const char* e = getenv("LDMSEG_GN_MINPX");
+    min_px_env = e ? atoi(e) : 0;
+  }
+  const int min_px = min_px_env > 0 ? min_px_env : (hw <= 256 ? 1 : 4);
+  int cmax = (hw + min_px * lanes - 1) / (min_px * lanes);
   if (chunks > cmax) chunks = cmax;
   if (chunks < 1) chunks = 1;
   int ppc = (hw + chunks - 1) / chunks;
