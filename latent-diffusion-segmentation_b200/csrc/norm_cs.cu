@@ -205,7 +205,17 @@ static int gn_apply_cs_launch(const void* src0, int c0, const float* chan_stats0
     const char* e = getenv("LDMSEG_GN_MINPX");
     min_px_env = e ? atoi(e) : 0;
   }
-  const int min_px = min_px_env > 0 ? min_px_env : (hw <= 256 ? 1 : 4);
+  static int mid_env = -1;
+  if (mid_env < 0) {
+    const char* e = getenv("LDMSEG_GN_MINPX_MID");
+    mid_env = e ? atoi(e) : 1;
+  }
+  static int top_env = -1;
+  if (top_env < 0) {
+    const char* e = getenv("LDMSEG_GN_MINPX_TOP");
+    top_env = e ? atoi(e) : 4;
+  }
+  const int min_px = min_px_env > 0 ? min_px_env : (hw <= 256 ? 1 : hw <= 1024 ? mid_env : top_env);
   int cmax = (hw + min_px * lanes - 1) / (min_px * lanes);
   if (chunks > cmax) chunks = cmax;
   if (chunks < 1) chunks = 1;
