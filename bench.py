@@ -323,7 +323,8 @@ def kernel_roofline(plan, peaks):
     for p in params:
         m = p.nb * p.h * p.w
         k = sum(p.seg_taps[i] * p.src_c[p.seg_src[i]] for i in range(p.nseg))
-        flops += 2.0 * m * p.n * k
+        # executed multiply-adds: a folded up-sampling launch runs 4 phase GEMMs of 4 taps over its (input) rows
+        flops += 2.0 * m * p.n * k * (4 if p.upsample2 else 1)
     is_ig = [t.startswith("igemm:") for t in plan.tags]
 
     def runner(skip_igemm):

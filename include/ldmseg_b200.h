@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LDMSEG_ABI_VERSION 3
+#define LDMSEG_ABI_VERSION 4
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ldmseg_version(void);
@@ -63,7 +63,7 @@ typedef struct ldmseg_igemm_params {
   /* K segments, in weight order */
   int nseg;
   int seg_src[LDMSEG_MAX_SEG];       /* index into src[] */
-  int seg_taps[LDMSEG_MAX_SEG];      /* 1 or 9 */
+  int seg_taps[LDMSEG_MAX_SEG];      /* 1 or 9 (4: see upsample2) */
   /* B operand */
   const void* weight;                /* bf16 [n, ktot] */
   int n;                             /* output channels */
@@ -79,7 +79,8 @@ typedef struct ldmseg_igemm_params {
   int out_dtype;                     /* LDMSEG_OUT_* */
   int act;                           /* LDMSEG_ACT_* */
   /* scheduling */
-  int block_n;                       /* 0 = choose; else 64 / 128 / 160 / 256 */
+  int block_n;                       /* 0 = choose; else 64 / 128 / 160 / 256; 320 with `pair` only (two N = 160
+                                        tcgen05.mma per k-step sharing the staged A rows; no split_k, no GEGLU) */
   int split_k;                       /* 0/1 = none; >1 needs workspace */
   float* workspace;                  /* split-K partial tiles, f32, tiles*split_k*128*block_n elements */
   int* tile_counters;                /* split-K: 8192 int32, zero-initialised once (self-resetting) */
@@ -95,7 +96,7 @@ typedef struct ldmseg_igemm_params {
                                         with the previous kernel's tail) */
   int pair;                          /* 1: CTA pairs (clusters of 2, tcgen05 cta_group::2): 256 x block_n tiles, each
                                         CTA stages its 128 rows of A and half of the B tile.  Needs weight_tiled,
-                                        block_n in {128, 160, 256} and M > 128 */
+                                        block_n in {128, 160, 256, 320} and M > 128 */
   /* ---- ABI version 2 ---- */
   int weight_static;                 /* 1: nothing on the stream writes `weight` (real parameters), so its first
                                         tiles may be fetched BEFORE the grid-dependency wait under `pdl`.  Must be 0
@@ -133,6 +134,20 @@ typedef struct ldmseg_igemm_params {
                                         memory instead of `workspace` (which is then unused).  Falls back to the
                                         workspace exchange when the device cannot hold all the tiles' clusters at once
                                         (see ldmseg_igemm_max_split_clusters) */
+  /* ---- ABI version 4 ---- */
+  int upsample2;                     /* 1: nearest x2 up-sampling folded into the 3x3 convolution that follows it
+                                        (diffusers Upsample2D = F.interpolate(scale_factor=2, mode="nearest") + conv,
+                                        reached from ldmseg/models/unet.py:401-425).  (nb, h, w) is the INPUT geometry,
+                                        `out` is [nb*2h*2w, out_ld].  The launch runs four phase GEMMs over the input
+                                        pixels: output pixel (2y+py, 2x+px) is a 2x2 convolution of the input whose
+                                        tap (a, b) reads (y+py+a-1, x+px+b-1) with the sum of the 3x3 taps that land
+                                        there -- 4/9 of the multiply-adds and no up-sampled tensor.  One segment with
+                                        seg_taps = 4; `weight` = the four phase matrices (phase = 2*py+px) stacked along
+                                        n, block-tiled: [4*ceil(n/16)][4*roundup(c,64)/64][16][64]; ktot =
+                                        4*roundup(c,64).  `stats_hw` counts INPUT rows per image.  Bias, SiLU, f32 /
+                                        shadow outputs, split_k, stream_k, pair (even number of 128-row input tiles)
+                                        and fused statistics are supported; residual / rowbias / LayerNorm folds /
+                                        GEGLU / conv_stride 2 are not */
 } ldmseg_igemm_params;
 
 int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream);

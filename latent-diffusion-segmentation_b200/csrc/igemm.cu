@@ -21,6 +21,7 @@
 #include "common.h"
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "ptx.cuh"
 #include "../../include/ldmseg_b200.h"
 
@@ -82,6 +83,9 @@ struct alignas(64) IgemmKParams {
   int tail_tiles;
   int tail_slots;      // workspace slots (partial tiles) per tail tile
   int vec_ok;         // out / residual pointers and leading dimensions allow 32-byte vector accesses
+  int up2;            // nearest x2 up-sampling folded into the 3x3 convolution: the launch runs 4 phase GEMMs, phase
+  int up_m_tiles;     // (py, px) = the output pixels (2y + py, 2x + px) as a 2x2 convolution of the h x w input;
+  int up_nblk;        // num_m_tiles = 4 * up_m_tiles (phase-major); up_nblk = 16-row weight blocks per phase
   int debug;          // development only (ldmseg_set_debug; timing experiments, results are garbage):
                       // bit0 split-K without the final reduce, bit1 without publish / wait / reduce, bit2 without the
                       // partial store; bit3 / bit4 leave the A / B loads out after a work item's first k-block; bit5 drop
@@ -92,8 +96,21 @@ struct alignas(64) IgemmKParams {
 // PAIR: two CTAs of a cluster work as one 256 x BN tile (tcgen05 cta_group::2): each CTA stages its own 128 rows of
 // A and HALF of the B tile, so a k-block costs 16 KB + BN * 64 B of shared-memory ingest per SM instead of
 // 16 KB + BN * 128 B -- operand ingest, not the tensor pipe, is what bounds the 1-CTA kernel (plan.py).
+//
+// BN = 320 (PAIR only): one tcgen05.mma is at most 256 wide, so a k-step issues TWO N = 160 instructions that share the
+// staged A rows -- per multiply-add a third less shared-memory traffic than two 160-wide tiles (A is filled and
+// fetched once for 320 columns), which is what bounds the N = 320 / 640 / 1280 convolutions.  2 x 320 accumulator
+// columns do not fit the 512 of tensor memory, so the accumulators live in THREE 160-column slots used as a ring:
+// tile i takes ring positions 2i, 2i + 1 (slots mod 3).  Tile i + 1's first half lands in the slot tile i never
+// touched, its second half in the slot tile i's epilogue drains FIRST, and the MMA issuer runs the first-half
+// instructions of a tile's first k-blocks ahead of the second-half ones (the stages stay occupied meanwhile), so the
+// tensor core keeps working while that slot drains.
 template <int BN, bool PAIR = false>
 struct IgemmCfg {
+  static_assert(BN != 320 || PAIR, "the 320-wide tile is built for CTA pairs");
+  static constexpr int kSub = BN == 320 ? 2 : 1;      // tcgen05.mma instructions per k-step and tile
+  static constexpr int kSubN = BN / kSub;             // their width
+  static constexpr int kAccSlots = BN == 320 ? 3 : 2; // accumulator slots of kSubN columns in tensor memory
   static constexpr int kBRows = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -101,8 +118,9 @@ struct IgemmCfg {
   static constexpr int kStages = PAIR ? ((BN <= 160) ? 8 : 6)
                                       : (BN <= 64) ? 9 : (BN <= 128) ? 7 : (BN <= 160) ? 6 : 4;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  // stages + barriers (2*stages + 4) * 8 + tmem ptr, + 1024 alignment slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+  // stages + barriers (2*stages + 2 + slots) * 8 + tmem ptr, + 1024 alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 2 + kAccSlots) * 8 + 16 + 1024;
+  static_assert(kSmemBytes <= 232448, "over the 227 KB of shared memory a CTA may use");
 };
 
 // ---- epilogue ------------------------------------------------------------------------------
@@ -163,6 +181,7 @@ __device__ __forceinline__ float2 fast_gelu2(float2 x) {
 // made every access a load the compiler had to repeat after each global store).
 struct EpiArgs {
   int M, N, HW, out_ld, res_ld, rowbias_ld, act, out_f32, split_k, stats_hw, vec_ok, res_f32, out2_ld;
+  int up_w, up_off;   // folded x2 up-sampling: input width (0 = off) and this phase's 2 * py * w + px
   float ln_inv_c, ln_eps;
   float* rowstats;
   const float* ln_rowstats;
@@ -198,6 +217,9 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
                                            int col0, int lane, float ln_mu, float ln_r, float& rs1, float& rs2) {
   const bool row_ok = m < p.M;
   const bool full = (col0 + 32 <= p.N) && p.vec_ok;
+  // row of `out` this accumulator row lands in: m itself, or -- folded x2 up-sampling, m = (n, y, x) of the INPUT --
+  // pixel (2y + py, 2x + px) of the output:  n 4hw + (2y + py) 2w + 2x + px  =  4m - 2x + (2 py w + px)
+  const size_t mo = p.up_w ? static_cast<size_t>(4 * m - 2 * (m % p.up_w) + p.up_off) : static_cast<size_t>(m);
   if (full) {
     if (kEpiLnFold && p.ln_colsum != nullptr) {
       const float nmr = -ln_mu * ln_r;
@@ -235,7 +257,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
         o[i] = pack_bf16x2(r.x, r.y);
       }
       if (row_ok)
-        stg256(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + (col0 >> 1), o);
+        stg256(reinterpret_cast<__nv_bfloat16*>(p.out) + mo * p.out_ld + (col0 >> 1), o);
       return;
     } else {
       if (p.residual != nullptr && row_ok) {
@@ -281,7 +303,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
       }
       if (p.out_f32) {
         if (row_ok) {
-          float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + col0;
+          float* op = reinterpret_cast<float*>(p.out) + mo * p.out_ld + col0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) stg256(op + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&v[8 * j]));
           if (p.out2 != nullptr) {   // bf16 shadow for the consumers that read this tensor through TMA
@@ -291,7 +313,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
               o0[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
               o1[i] = pack_bf16x2(v[16 + 2 * i], v[17 + 2 * i]);
             }
-            __nv_bfloat16* o2 = p.out2 + static_cast<size_t>(m) * p.out2_ld + col0;
+            __nv_bfloat16* o2 = p.out2 + mo * p.out2_ld + col0;
             stg256(o2, o0);
             stg256(o2 + 16, o1);
           }
@@ -304,7 +326,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
           o1[i] = pack_bf16x2(v[16 + 2 * i], v[17 + 2 * i]);
         }
         if (row_ok) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_ld + col0;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + mo * p.out_ld + col0;
           stg256(op, o0);
           stg256(op + 16, o1);
         }
@@ -338,11 +360,11 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
                              p.residual)[static_cast<size_t>(m) * p.res_ld + col]);
       if (p.act == LDMSEG_ACT_SILU) x = fast_silu(x);
       if (p.out_f32) {
-        reinterpret_cast<float*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = x;
-        if (p.out2 != nullptr) p.out2[static_cast<size_t>(m) * p.out2_ld + col] = __float2bfloat16(x);
+        reinterpret_cast<float*>(p.out)[mo * p.out_ld + col] = x;
+        if (p.out2 != nullptr) p.out2[mo * p.out2_ld + col] = __float2bfloat16(x);
       } else {
         const __nv_bfloat16 o = __float2bfloat16(x);
-        reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<size_t>(m) * p.out_ld + col] = o;
+        reinterpret_cast<__nv_bfloat16*>(p.out)[mo * p.out_ld + col] = o;
         x = __bfloat162float(o);
       }
       if (p.rowstats != nullptr) {
@@ -379,11 +401,13 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& p, float (&v)[32], int
 //   FINAL  : sum of the workspace partials -> epilogue -> global, for the chunks dealt to this split
 //   DIRECT_ADD: TMEM + the first `split_idx` workspace partials -> epilogue -> global (stream-K tail: the CTA that
 //               holds a tile's last k-blocks finishes it)
+// ws_stride: f32 elements between two partials of the tile in the workspace (BM x the tile's full width)
 template <int BN, bool GEGLU, int MODE, int NH>
 __device__ __forceinline__ void epilogue_warp(const EpiArgs& p, uint32_t t_row, float* ws_tile, int split_idx,
-                                              int m_base, int n0, int q, int half, int lane, float2 ln_rs) {
+                                              int m_base, int n0, int q, int half, int lane, float2 ln_rs,
+                                              int ws_stride = BM * BN) {
   constexpr int kChunks = BN / 32;
-  constexpr int kTileElems = BM * BN;
+  const size_t kTileElems = static_cast<size_t>(ws_stride);
   const int m = m_base + lane;
   const int row_in_tile = q * 32 + lane;
   const int img = m / p.HW;                                       // image of this row (per-image bias)
@@ -697,6 +721,7 @@ __global__ void __launch_bounds__(igemm_threads(GEGLU, SPLIT), 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
   static_assert(!(TAIL && (SPLIT || GEGLU)), "the stream-K tail replaces split-K; it is not built for GEGLU");
   static_assert(!CSPLIT || (SPLIT && !PAIR && !TAIL), "the cluster exchange is a form of split-K for single CTAs");
+  static_assert(BN != 320 || (PAIR && !SPLIT && !GEGLU), "the 320-wide tile: CTA pairs, whole tiles or the stream-K tail");
   using Cfg = IgemmCfg<BN, PAIR>;
   constexpr int kEpiWarps = igemm_epi_warps(GEGLU, SPLIT);
   constexpr int kEpiThreads = kEpiWarps * 32;
@@ -711,8 +736,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + 2;   // one per accumulator slot
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::kAccSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -728,10 +753,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiThreads : kEpiThreads);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&tmem_full[i], 1);
+    for (int i = 0; i < Cfg::kAccSlots; ++i) mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiThreads : kEpiThreads);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -807,16 +830,29 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       auto arm = [&](int stage, uint32_t cta_bytes = Cfg::kStageBytes) {
         if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], PAIR ? 2 * cta_bytes : cta_bytes);
       };
-      auto load_b = [&](int stage, int kb, int n_tile) {
+      // blk0: first 16-row weight block of the launch's phase (folded up-sampling: the 4 phase matrices are stacked
+      // along N, block-tiled weights only), else 0
+      auto load_b = [&](int stage, int kb, int n_tile, int blk0) {
         if constexpr (PAIR) {
-          tma_load_4d_2sm(smem_b + stage * Cfg::kBBytes, &p.b_map, full0 + stage * 8, 0, 0, kb,
-                          n_tile * (BN / 16) + static_cast<int>(rank) * (BN / 32));
+          // per tcgen05.mma of the k-step (one, or two for BN = 320): this CTA's half of that instruction's B rows
+#pragma unroll
+          for (int j = 0; j < Cfg::kSub; ++j)
+            tma_load_4d_2sm(smem_b + stage * Cfg::kBBytes + j * (Cfg::kBBytes / Cfg::kSub), &p.b_map,
+                            full0 + stage * 8, 0, 0, kb,
+                            blk0 + n_tile * (BN / 16) + j * (Cfg::kSubN / 16) +
+                                static_cast<int>(rank) * (Cfg::kSubN / 32));
         } else {
           if (p.w_tiled)
-            tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb, n_tile * (BN / 16));
+            tma_load_4d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], 0, 0, kb,
+                        blk0 + n_tile * (BN / 16));
           else
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * BK, n_tile * BN);
         }
+      };
+      // (virtual) 128-row tile -> up-sampling phase 2 py + px (0 for every other launch)
+      auto phase_of = [&](int unit_tile) {
+        const int m_unit = unit_tile / p.num_n_tiles;
+        return p.up2 ? (PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit) / p.up_m_tiles : 0;
       };
       // Weights are never written inside the stream, so their loads need not wait for the previous kernel:
       // the first work item's weight tiles go into the (still empty) ring while the predecessor is still running
@@ -826,10 +862,11 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       int tile, split, kb_begin, kb_end, slot;
       if (p.prefetch_b && get_item(0, tile, split, kb_begin, kb_end, slot)) {
         const int n_tile = tile % p.num_n_tiles;
+        const int blk0 = phase_of(tile) * p.up_nblk;
         prefetched = min(kStages, kb_end - kb_begin);
         for (int i = 0; i < prefetched; ++i) {
           arm(i);
-          load_b(i, kb_begin + i, n_tile);
+          load_b(i, kb_begin + i, n_tile, blk0);
         }
       }
       pdl_wait();  // activations (and everything else the predecessor wrote) from here on
@@ -838,7 +875,13 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       for (int it = 0; get_item(it, tile, split, kb_begin, kb_end, slot); ++it) {
         const int m_unit = tile / p.num_n_tiles;
         const int n_tile = tile - m_unit * p.num_n_tiles;
-        const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
+        int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
+        int up_ph = 0;   // up-sampling phase 2 py + px
+        if (p.up2) {     // phase-major virtual tiles: 128 INPUT pixels, output pixels (2y + py, 2x + px)
+          up_ph = m_tile / p.up_m_tiles;
+          m_tile -= up_ph * p.up_m_tiles;
+        }
+        const int blk0 = up_ph * p.up_nblk;
         const int m0 = m_tile * BM;
         const int x0 = (m0 % p.W) * p.a_stride;
         const int y0 = ((m0 / p.W) % p.H) * p.a_stride;
@@ -865,6 +908,9 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           if (p.seg_taps[seg] == 9) {
             dy = tap / 3 - p.a_pad;
             dx = tap - (tap / 3) * 3 - p.a_pad;
+          } else if (p.seg_taps[seg] == 4) {   // 2x2 phase kernel: tap (a, b) reads input (y + py + a - 1, x + px + b - 1)
+            dy = (tap >> 1) + (up_ph >> 1) - 1;
+            dx = (tap & 1) + (up_ph & 1) - 1;
           }
           if (!skip_a) {
             if constexpr (PAIR)
@@ -874,7 +920,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
               tma_load_4d(smem_a + stage * kABytes, &p.a_map[p.seg_src[seg]], &full_bar[stage],
                           cb * BK, x0 + dx, y0 + dy, b0);
           }
-          if (!b_done && !skip_b) load_b(stage, kb, n_tile);
+          if (!b_done && !skip_b) load_b(stage, kb, n_tile, blk0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -909,7 +955,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if ((!PAIR || rank == 0) && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, Cfg::kSubN, 0, 0);
       // descriptor = constant fields + start address >> 4 (stage s adds s * stage bytes >> 4; never carries out
       // of the 14-bit field: shared memory is < 256 KB)
       const uint64_t desc_base = make_smem_desc_sw128(0, 16, 1024);
@@ -920,6 +966,66 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
       for (int it = 0; get_item(it, tile, split, kb_begin, kb_end, slot); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        if constexpr (Cfg::kSub == 2) {
+          // 320-wide tile: halves into the ring slots r0 = 2 it and r1 = 2 it + 1 (mod 3).  Slot r1 is the one the
+          // previous tile's epilogue drains first; until it is free, run the first-half MMAs of the tile's first
+          // k-blocks ahead (their stages stay occupied), then catch up with the second halves and release the stages.
+          const int r0 = 2 * it, r1 = 2 * it + 1;
+          const int s0 = r0 % 3, s1 = r1 % 3;
+          mbar_wait(&tmem_empty[s0], ((r0 / 3) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + s0 * Cfg::kSubN, d1 = tmem_base + s1 * Cfg::kSubN;
+          constexpr uint32_t kSubDesc = (Cfg::kBBytes / 2) >> 4;   // second half of the stage's B rows
+          const int nkb = kb_end - kb_begin;
+          const int ahead = nkb < kStages - 1 ? nkb : kStages - 1;
+          int st = stage;
+          uint32_t ph = phase;
+          for (int i = 0; i < ahead; ++i) {
+            mbar_wait(&full_bar[st], ph);
+            tc_fence_after();
+            const uint64_t adesc = desc_base + (a_lo + st * (kABytes >> 4));
+            const uint64_t bdesc = desc_base + (b_lo + st * (Cfg::kBBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(d0, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (++st == kStages) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+          mbar_wait(&tmem_empty[s1], ((r1 / 3) & 1) ^ 1);
+          tc_fence_after();
+          for (int i = 0; i < ahead; ++i) {
+            const uint64_t adesc = desc_base + (a_lo + stage * (kABytes >> 4));
+            const uint64_t bdesc = desc_base + (b_lo + stage * (Cfg::kBBytes >> 4)) + kSubDesc;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(d1, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          for (int kb = kb_begin + ahead; kb < kb_end; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = desc_base + (a_lo + stage * (kABytes >> 4));
+            const uint64_t bdesc = desc_base + (b_lo + stage * (Cfg::kBBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_2sm(d0, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+              umma_bf16_2sm(d1, adesc + 2 * k, bdesc + kSubDesc + 2 * k, idesc, 1u);
+            }
+            umma_commit_2sm(&empty_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit_2sm(&tmem_full[acc]);
+          continue;
+        }
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -973,17 +1079,51 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     ea.res_f32 = p.res_f32; ea.out2 = p.out2; ea.out2_ld = p.out2_ld;
     ea.rowstats = p.rowstats; ea.ln_rowstats = p.ln_rowstats; ea.ln_colsum = p.ln_colsum;
     ea.ln_inv_c = p.ln_inv_c; ea.ln_eps = p.ln_eps;
+    ea.up_w = p.up2 ? p.W : 0; ea.up_off = 0;
     const uint32_t tmem_empty0 = PAIR ? map_to_cta(&tmem_empty[0], 0) : 0u;   // the leader's barrier
     auto release_acc = [&](int acc) {
       if constexpr (PAIR) mbar_arrive_cluster(tmem_empty0 + acc * 8);
       else mbar_arrive(&tmem_empty[acc]);
     };
+    // One tile's accumulator through epilogue_warp<MODE> and back to the MMA issuer.  320-wide tiles: the two 160-wide
+    // halves one after the other (ring slots 2 it, 2 it + 1 mod 3), each slot released as soon as it is drained -- the
+    // next tile's second half is waiting for the FIRST one; the warps of a quadrant swap their chunk parity for the
+    // second half (5 chunks per half: 3 + 2 each way).
+    auto run_epilogue = [&](auto mode, int it, uint32_t t_row, float* ws_tile, int sidx, int m_base, int n0, int q,
+                            int half, float2 ln_rs) {
+      constexpr int MODE = decltype(mode)::value;
+      if constexpr (Cfg::kSub == 1) {
+        epilogue_warp<BN, GEGLU, MODE, NH>(ea, t_row, ws_tile, sidx, m_base, n0, q, half, lane, ln_rs);
+        tc_fence_before();
+        release_acc(it & 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int s = (2 * it + j) % 3;
+          epilogue_warp<Cfg::kSubN, GEGLU, MODE, NH>(
+              ea, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * Cfg::kSubN,
+              ws_tile != nullptr ? ws_tile + j * (BM * Cfg::kSubN) : nullptr, sidx, m_base, n0 + j * Cfg::kSubN, q,
+              half ^ j, lane, ln_rs, BM * BN);
+          tc_fence_before();
+          release_acc(s);
+        }
+      }
+    };
+    using ModeDirect = std::integral_constant<int, EPI_DIRECT>;
+    using ModePartial = std::integral_constant<int, EPI_PARTIAL>;
+    using ModeDirectAdd = std::integral_constant<int, EPI_DIRECT_ADD>;
     int unit_tile, split, kb_begin_, kb_end_, slot;
     for (int it = 0; get_item(it, unit_tile, split, kb_begin_, kb_end_, slot); ++it) {
       const int m_unit = unit_tile / p.num_n_tiles;
       const int n_tile = unit_tile - m_unit * p.num_n_tiles;
-      const int m_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
-      const int tile = m_tile * p.num_n_tiles + n_tile;   // 128-row output tile (split-K workspace / counters)
+      const int vm_tile = PAIR ? 2 * m_unit + static_cast<int>(rank) : m_unit;
+      const int tile = vm_tile * p.num_n_tiles + n_tile;   // 128-row output tile (split-K workspace / counters)
+      int m_tile = vm_tile;   // 128 rows of M (folded up-sampling: of the INPUT pixels; vm_tile = phase-major)
+      if (p.up2) {
+        const int up_ph = vm_tile / p.up_m_tiles;
+        m_tile -= up_ph * p.up_m_tiles;
+        ea.up_off = (up_ph >> 1) * 2 * p.W + (up_ph & 1);
+      }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_base = m_tile * BM + q * 32;
@@ -1062,9 +1202,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         float* ws_tile = p.workspace + static_cast<size_t>(tt > 0 ? tt : 0) * p.tail_slots * (BM * BN);
         if (split == 1) {
           // a piece that ends inside the tile: publish the partial accumulator
-          epilogue_warp<BN, GEGLU, EPI_PARTIAL, NH>(ea, t_row, ws_tile, slot, m_base, n0, q, half, lane, ln_rs);
-          tc_fence_before();
-          release_acc(acc);
+          run_epilogue(ModePartial{}, it, t_row, ws_tile, slot, m_base, n0, q, half, ln_rs);
           asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread's stores before thread 0's release
           if (et == 0) {
             int seen;
@@ -1081,25 +1219,24 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
             } while (seen < slot);
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          epilogue_warp<BN, GEGLU, EPI_DIRECT_ADD, NH>(ea, t_row, ws_tile, slot, m_base, n0, q, half, lane, ln_rs);
-          tc_fence_before();
-          release_acc(acc);
+          run_epilogue(ModeDirectAdd{}, it, t_row, ws_tile, slot, m_base, n0, q, half, ln_rs);
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (et == 0) p.counters[tt] = 0;   // re-armed for the next launch (all `slot` arrivals were consumed)
         } else {
-          epilogue_warp<BN, GEGLU, EPI_DIRECT, NH>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane, ln_rs);
-          tc_fence_before();
-          release_acc(acc);
+          run_epilogue(ModeDirect{}, it, t_row, nullptr, 0, m_base, n0, q, half, ln_rs);
         }
       } else if constexpr (!SPLIT) {
         if (p.debug & 32) {   // development only: drop the tile (is the epilogue the bottleneck?)
           tc_fence_before();
-          release_acc(acc);
+          if constexpr (Cfg::kSub == 1) {
+            release_acc(acc);
+          } else {
+            release_acc((2 * it) % 3);
+            release_acc((2 * it + 1) % 3);
+          }
           continue;
         }
-        epilogue_warp<BN, GEGLU, EPI_DIRECT, NH>(ea, t_row, nullptr, 0, m_base, n0, q, half, lane, ln_rs);
-        tc_fence_before();
-        release_acc(acc);
+        run_epilogue(ModeDirect{}, it, t_row, nullptr, 0, m_base, n0, q, half, ln_rs);
       } else {
         // split-K: every split stores its partial tile (coalesced, no atomics); once all splits of the
         // tile have arrived, each split CTA reduces and finishes its share of the tile's chunks.
@@ -1268,7 +1405,8 @@ static int validate(const ldmseg_igemm_params* p) {
   int ktot = 0;
   for (int s = 0; s < p->nseg; ++s) {
     LDM_REQUIRE(p->seg_src[s] >= 0 && p->seg_src[s] < p->nsrc, "igemm: bad seg_src");
-    LDM_REQUIRE(p->seg_taps[s] == 1 || p->seg_taps[s] == 9, "igemm: taps must be 1 or 9");
+    LDM_REQUIRE(p->seg_taps[s] == 1 || p->seg_taps[s] == 9 || (p->upsample2 && p->seg_taps[s] == 4),
+                "igemm: taps must be 1 or 9 (4 with upsample2)");
     const int c = p->src_c[p->seg_src[s]];
     LDM_REQUIRE(c > 0 && c % 8 == 0, "igemm: source channels must be a multiple of 8 (got %d)", c);
     ktot += p->seg_taps[s] * ((c + BK - 1) / BK * BK);
@@ -1295,6 +1433,16 @@ static int validate(const ldmseg_igemm_params* p) {
   if (p->conv_stride == 2) {
     LDM_REQUIRE(p->conv_pad == 0 || p->conv_pad == 1, "igemm: stride-2 conv_pad must be 0 or 1");
     for (int s = 0; s < p->nseg; ++s) LDM_REQUIRE(p->seg_taps[s] == 9, "igemm: stride 2 is defined for 3x3 segments only");
+  }
+  if (p->upsample2) {
+    LDM_REQUIRE(p->nseg == 1 && p->seg_taps[0] == 4, "igemm: upsample2 takes one segment with 4 taps");
+    LDM_REQUIRE(p->weight_tiled, "igemm: upsample2 needs block-tiled weights (4 phase matrices stacked along n)");
+    LDM_REQUIRE(p->conv_stride != 2 && p->act != LDMSEG_ACT_GEGLU && !p->residual && !p->rowbias && !p->rowstats_out &&
+                    !p->ln_colsum && !p->ln_rowstats,
+                "igemm: upsample2 supports bias, SiLU, f32 / shadow outputs and fused statistics only");
+    if (p->pair)
+      LDM_REQUIRE(((static_cast<long long>(p->nb) * p->h * p->w + BM - 1) / BM) % 2 == 0,
+                  "igemm: upsample2 in pair mode needs an even number of 128-row input tiles (a pair shares one phase)");
   }
   if (p->out2) {
     LDM_REQUIRE(p->out_dtype == LDMSEG_OUT_F32 && p->act != LDMSEG_ACT_GEGLU, "igemm: out2 (bf16 shadow) needs an f32 out");
@@ -1429,16 +1577,23 @@ static int csplit_max_clusters(int bn, bool geglu, int cluster_size) {
 template <int BN, bool PAIR>
 static int launch_igemm(const IgemmKParams& kp, int grid, cudaStream_t stream, int pdl) {
   const bool geglu = kp.act == LDMSEG_ACT_GEGLU, split = kp.split_k > 1;
-  if (kp.tail) return launch_igemm_v<BN, false, false, PAIR, true>(kp, grid, stream, pdl);
-  if constexpr (!PAIR) {
-    if (kp.csplit)
-      return geglu ? launch_igemm_v<BN, true, true, false, false, true>(kp, grid, stream, pdl)
-                   : launch_igemm_v<BN, false, true, false, false, true>(kp, grid, stream, pdl);
+  if constexpr (BN == 320) {   // whole tiles or the stream-K tail only (validated by the caller)
+    (void)geglu;
+    (void)split;
+    return kp.tail ? launch_igemm_v<BN, false, false, true, true>(kp, grid, stream, pdl)
+                   : launch_igemm_v<BN, false, false, true, false>(kp, grid, stream, pdl);
+  } else {
+    if (kp.tail) return launch_igemm_v<BN, false, false, PAIR, true>(kp, grid, stream, pdl);
+    if constexpr (!PAIR) {
+      if (kp.csplit)
+        return geglu ? launch_igemm_v<BN, true, true, false, false, true>(kp, grid, stream, pdl)
+                     : launch_igemm_v<BN, false, true, false, false, true>(kp, grid, stream, pdl);
+    }
+    if (geglu) return split ? launch_igemm_v<BN, true, true, PAIR>(kp, grid, stream, pdl)
+                            : launch_igemm_v<BN, true, false, PAIR>(kp, grid, stream, pdl);
+    return split ? launch_igemm_v<BN, false, true, PAIR>(kp, grid, stream, pdl)
+                 : launch_igemm_v<BN, false, false, PAIR>(kp, grid, stream, pdl);
   }
-  if (geglu) return split ? launch_igemm_v<BN, true, true, PAIR>(kp, grid, stream, pdl)
-                          : launch_igemm_v<BN, true, false, PAIR>(kp, grid, stream, pdl);
-  return split ? launch_igemm_v<BN, false, true, PAIR>(kp, grid, stream, pdl)
-               : launch_igemm_v<BN, false, false, PAIR>(kp, grid, stream, pdl);
 }
 
 static int choose_block_n(int m_tiles, int n, int sms) {
@@ -1490,25 +1645,35 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
   }
   kp.a_stride = static_cast<int>(cs);
   kp.a_pad = cs == 2 ? p->conv_pad : 1;
-  const int m_tiles = (M + BM - 1) / BM;
+  // folded x2 up-sampling: 4 phase GEMMs over the input pixels, laid out as 4 x as many (phase-major) 128-row tiles
+  const int up2 = p->upsample2 ? 1 : 0;
+  const int m_tiles = (up2 ? 4 : 1) * ((M + BM - 1) / BM);
+  kp.up2 = up2;
+  kp.up_m_tiles = (M + BM - 1) / BM;
+  kp.up_nblk = up2 ? (p->n + 15) / 16 : 0;
   int bn = p->block_n;
   if (bn == 0) bn = choose_block_n(m_tiles, p->n, num_sms());
-  LDM_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "igemm: unsupported block_n %d", bn);
+  LDM_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256 || bn == 320, "igemm: unsupported block_n %d", bn);
   const bool pair = p->pair != 0;
   if (pair) {
     LDM_REQUIRE(p->weight_tiled, "igemm: pair mode needs block-tiled weights");
-    LDM_REQUIRE(bn == 128 || bn == 160 || bn == 256, "igemm: pair mode supports block_n 128 / 160 / 256 (got %d)", bn);
+    LDM_REQUIRE(bn == 128 || bn == 160 || bn == 256 || bn == 320,
+                "igemm: pair mode supports block_n 128 / 160 / 256 / 320 (got %d)", bn);
     LDM_REQUIRE(m_tiles >= 2, "igemm: pair mode needs at least two 128-row tiles");
   }
+  if (bn == 320)
+    LDM_REQUIRE(pair && p->split_k <= 1 && p->act != LDMSEG_ACT_GEGLU && !p->split_cluster,
+                "igemm: block_n 320 needs pair mode, no split_k, no GEGLU");
   {
     if (p->weight_tiled) {
       // [N/16][K/64][16][64]: every 16-row x 64-k block is 2 KB contiguous -> weight streaming reads
       // whole DRAM pages instead of 128-byte pieces at a K-row stride; a CTA of a pair stages half a tile
       // (bn / 2 rows: 80 for bn = 160, hence 16-row blocks)
       const uint64_t kblocks = static_cast<uint64_t>(p->ktot) / BK;
-      uint64_t dims[4] = {BK, 16, kblocks, static_cast<uint64_t>((p->n + 15) / 16)};
+      uint64_t dims[4] = {BK, 16, kblocks, static_cast<uint64_t>((up2 ? 4 : 1) * ((p->n + 15) / 16))};
       uint64_t strides[3] = {128, 2048, kblocks * 2048};
-      uint32_t box[4] = {BK, 16, 1, static_cast<uint32_t>(pair ? bn / 32 : bn / 16)};
+      // (block_n 320: two N = 160 instructions per k-step, one box of 80 rows per CTA and instruction)
+      uint32_t box[4] = {BK, 16, 1, static_cast<uint32_t>(pair ? (bn == 320 ? 160 : bn) / 32 : bn / 16)};
       if (int rc = encode_tmap_bf16(&kp.b_map, p->weight, 4, dims, strides, box)) return rc;
     } else {
     uint64_t dims[2] = {static_cast<uint64_t>(p->ktot), static_cast<uint64_t>(p->n)};
@@ -1653,6 +1818,7 @@ extern "C" int ldmseg_igemm(const ldmseg_igemm_params* p, void* stream) {
     switch (bn) {
       case 128: return launch_igemm<128, true>(kp, grid, st, p->pdl);
       case 160: return launch_igemm<160, true>(kp, grid, st, p->pdl);
+      case 320: return launch_igemm<320, true>(kp, grid, st, p->pdl);
       default: return launch_igemm<256, true>(kp, grid, st, p->pdl);
     }
   }
@@ -1673,6 +1839,7 @@ extern "C" int ldmseg_igemm_max_split_clusters(int block_n, int geglu, int clust
 
 extern "C" int ldmseg_igemm_simple(const ldmseg_igemm_params* p, void* stream) {
   if (int rc = validate(p)) return rc;
+  LDM_REQUIRE(!p->upsample2, "igemm_simple: upsample2 is not defined for the reference-grade kernel");
   const int M = p->nb * p->h * p->w;
   const long long total = static_cast<long long>(M) * p->n;
   const int threads = 256;

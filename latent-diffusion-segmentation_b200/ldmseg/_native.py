@@ -81,6 +81,7 @@ class IgemmParams(C.Structure):
         ("ln_eps", C.c_float),
         ("stream_k", C.c_int),
         ("split_cluster", C.c_int),
+        ("upsample2", C.c_int),
     ]
 
 
@@ -202,7 +203,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
                       conv_stride: int = 1, conv_pad: int = 1, rowstats_out: Optional[torch.Tensor] = None,
                       ln_rowstats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None,
                       ln_channels: int = 0, ln_eps: float = 0.0, stream_k: bool = False,
-                      split_cluster: bool = False) -> IgemmParams:
+                      split_cluster: bool = False, upsample2: bool = False) -> IgemmParams:
     p = IgemmParams()
     for i, s in enumerate(srcs):
         p.src[i] = s.data_ptr()
@@ -218,7 +219,8 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.weight = weight.data_ptr()
     p.n = n
     p.ktot = ktot
-    assert weight.numel() >= (((n + 15) // 16 * 16) if weight_tiled else n) * ktot, (weight.shape, n, ktot)
+    assert weight.numel() >= (4 if upsample2 else 1) * (((n + 15) // 16 * 16) if weight_tiled else n) * ktot, \
+        (weight.shape, n, ktot)
     p.bias = _ptr(bias)
     p.rowbias = _ptr(rowbias)
     p.rowbias_ld = rowbias_ld
@@ -253,6 +255,7 @@ def make_igemm_params(srcs: Sequence[torch.Tensor], src_c: Sequence[int], nb: in
     p.ln_eps = ln_eps
     p.stream_k = 1 if stream_k else 0
     p.split_cluster = 1 if split_cluster else 0
+    p.upsample2 = 1 if upsample2 else 0
     return p
 
 

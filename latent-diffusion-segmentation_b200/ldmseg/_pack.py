@@ -28,6 +28,30 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(n, 9 * cp)
 
 
+def pack_upsample2_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """Nearest x2 up-sampling folded into the 3x3 convolution that follows it (diffusers Upsample2D):
+    [N, C, 3, 3] -> [4 * pad16(N), 4 * pad64(C)], the four phase matrices stacked along N (phase = 2*py + px).
+    Output pixel (2y+py, 2x+px) reads the up-sampled rows 2y+py+ky-1, i.e. the input rows y-1, y, y for py = 0 and
+    y, y, y+1 for py = 1 (same along x), so it is a 2x2 convolution of the INPUT whose tap (a, b) reads
+    (y+py+a-1, x+px+b-1) with the sum of the 3x3 taps that land there (ldmseg_igemm_params.upsample2)."""
+    n, c, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    cp, npad = _pad64(c), (n + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS
+    wf = w.detach().float()
+    taps = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}      # phase bit -> 3x3 taps summed into 2x2 tap 0 / 1
+    out = torch.zeros(4, npad, 4, cp, dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for a in range(2):
+                for b in range(2):
+                    acc = torch.zeros(n, c, dtype=torch.float32, device=w.device)
+                    for ky in taps[py][a]:
+                        for kx in taps[px][b]:
+                            acc += wf[:, :, ky, kx]
+                    out[2 * py + px, :n, 2 * a + b, :c] = acc
+    return out.reshape(4 * npad, 4 * cp)
+
+
 def pack_conv3x3_im2col(w: torch.Tensor) -> torch.Tensor:
     """[N, C, 3, 3] -> [N, pad64(9*C)] for convs fed by the im2col kernel (taps contiguous, no per-tap
     padding; identical to pack_conv3x3 when C is a multiple of 64)."""

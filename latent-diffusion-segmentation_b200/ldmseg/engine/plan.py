@@ -39,6 +39,9 @@ STREAM_K = os.environ.get("LDMSEG_STREAM_K", "1") != "0"
 # UNet forward; profiles/r02_ab_cluster_splitk.log) -- moving a 64-128 KB fp32 partial tile per CTA over the SM-to-SM
 # network takes ~3 us, as long as the three L2 round trips it replaces; 1 = use it
 SPLIT_CLUSTER = os.environ.get("LDMSEG_SPLIT_CLUSTER", "0") != "0"
+# nearest x2 up-sampling folded into the 3x3 convolution after it (four 2x2 phase GEMMs over the input pixels, 4/9 of
+# the multiply-adds, no up-sampled tensor; ldmseg_igemm_params.upsample2); 0 = upsample2x kernel + plain 3x3 conv
+UP2_FOLD = os.environ.get("LDMSEG_UP2_FOLD", "1") != "0"
 
 
 USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
@@ -277,7 +280,7 @@ class PlanBase:
 
     def _gemm(self, layer: _Layer, srcs, src_c, nb, h, w, segs, out, *, rowbias=None, residual=None,
               act=nat.ACT_NONE, out_ld=None, bias="layer", allow_split=True, stream=False, shadow=True,
-              conv_stride=1, conv_pad=1, rowstats=None, ln=None):
+              conv_stride=1, conv_pad=1, rowstats=None, ln=None, upsample2=False):
         """Append one igemm launch.  `stream=True` marks `out` as a tensor of the residual stream: under
         RESID_F32 it is written as f32 (+ a bf16 shadow in `out` when `shadow`), and later `residual=` /
         GroupNorm / LayerNorm reads of `out` use the f32 copy."""
@@ -285,17 +288,24 @@ class PlanBase:
         m = nb * h * w
         tiled = bool(layer.extra.get("tiled", False))
         allow_split = allow_split and self.allow_split
+        allow_pair = USE_PAIR and tiled
+        if upsample2:
+            # (nb, h, w) is the INPUT geometry; the kernel runs 4 phases x ceil(m / 128) tiles of 128 input pixels and
+            # a CTA pair must stay inside one phase
+            assert layer.extra.get("up2", False) and tiled and segs == [(0, 4)], layer.extra.get("name")
+            allow_pair = allow_pair and ((m + 127) // 128) % 2 == 0
+            m = 4 * ((m + 127) // 128) * 128
         # the stream-K tail shares the split-K premise (a co-resident grid) and its scratch buffers
         tail_ok = STREAM_K and allow_split and tiled and act != nat.ACT_GEGLU
         geglu = act == nat.ACT_GEGLU
         cap = (lambda bn_, s_: nat.max_split_clusters(bn_, geglu, s_)) if SPLIT_CLUSTER and allow_split else None
         bn, split, pair, stream_k, split_cluster = choose_tiling_ex(
-            m, layer.n, num_kb, allow_split=allow_split, allow_pair=USE_PAIR and tiled, allow_tail=tail_ok,
+            m, layer.n, num_kb, allow_split=allow_split, allow_pair=allow_pair, allow_tail=tail_ok,
             cluster_cap=cap)
         tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
         if split > 1 and not split_cluster and tiles * split * 128 * bn > self.ws.numel():
             bn, split, pair, stream_k, split_cluster = choose_tiling_ex(
-                m, layer.n, num_kb, allow_split=False, allow_pair=USE_PAIR and tiled, allow_tail=False)
+                m, layer.n, num_kb, allow_split=False, allow_pair=allow_pair, allow_tail=False)
         out_main, out2 = out, None
         if stream and self.resid_f32 and out.dtype == torch.bfloat16:
             f = self._buf(out.shape[0], out.shape[1], torch.float32)
@@ -315,12 +325,12 @@ class PlanBase:
                                   ln_rowstats=None if ln is None else ln[0],
                                   ln_colsum=None if ln is None else layer.extra["ln_colsum"],
                                   ln_channels=0 if ln is None else ln[1], ln_eps=0.0 if ln is None else ln[2],
-                                  stream_k=stream_k, split_cluster=split_cluster)
+                                  stream_k=stream_k, split_cluster=split_cluster, upsample2=upsample2)
         self._keep.append(p)
         self._igemm_params.append((p, layer, m))
         if out.dtype == torch.bfloat16 and act != nat.ACT_GEGLU and out.is_contiguous():
             self._producer[out.data_ptr()] = (p, layer.n, out.shape[0])
-        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}:t{int(stream_k)}:c{int(split_cluster)}")
+        self._op(lambda p=p: nat.igemm(p), tag=f"igemm:{out.shape[0] if upsample2 else m}:{layer.extra.get('name', '')}:n{layer.n}:kb{num_kb}:bn{bn}:s{split}:p{int(pair)}:t{int(stream_k)}:c{int(split_cluster)}")
 
     def _down(self, layer: _Layer, x, c, h, pad_lo, act=nat.ACT_NONE):
         """3x3 stride-2 convolution of x [nb*h*h, c] -> [nb*(h/2)^2, n] (a tensor of the residual stream)."""
@@ -370,13 +380,15 @@ class PlanBase:
         prod = self._producer.get(key)
         if prod is None or prod[1] != c or prod[2] != self.nb * hw:
             return None
+        if prod[0].upsample2 and (hw // 4) % 32 != 0:
+            return None     # the producer's rows are INPUT pixels: a warp's 32 rows must stay inside one image
         need = self.nb * c * 2
         if self._arena_used + need > self.stats_arena.numel():
             return None
         sl = self.stats_arena[self._arena_used:self._arena_used + need]
         self._arena_used += need
         prod[0].stats = sl.data_ptr()          # the producer's launch happens later, at run time
-        prod[0].stats_hw = hw
+        prod[0].stats_hw = hw // 4 if prod[0].upsample2 else hw   # the kernel's rows: input pixels when it up-samples
         self._chan_stats[key] = sl
         return sl
 

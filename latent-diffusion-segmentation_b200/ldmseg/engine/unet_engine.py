@@ -23,7 +23,7 @@ import torch
 
 from ldmseg import _native as nat
 from ldmseg import _pack as pk
-from .plan import LN_FOLD, PlanBase, WeightsBase
+from .plan import LN_FOLD, UP2_FOLD, PlanBase, WeightsBase
 
 
 class UNetWeights(WeightsBase):
@@ -139,7 +139,10 @@ class UNetWeights(WeightsBase):
                     self._transformer(f"up{i}.attn{j}", blk.attentions[j])
             if blk.upsamplers is not None:
                 u = blk.upsamplers[0].conv
-                self._gemm(f"up{i}.up", pk.pack_conv3x3(u.weight), u.bias, u.out_channels)
+                if UP2_FOLD:   # nearest x2 folded into the conv: four 2x2 phase matrices (Upsample2D)
+                    self._gemm(f"up{i}.up", pk.pack_upsample2_conv3x3(u.weight), u.bias, u.out_channels, up2=True)
+                else:
+                    self._gemm(f"up{i}.up", pk.pack_conv3x3(u.weight), u.bias, u.out_channels)
         self._norm("norm_out", unet.conv_norm_out)
         self._gemm("conv_out", pk.pack_conv3x3(unet.conv_out.weight), unet.conv_out.bias, self.out_channels)
         self.tproj_w = self._dev(torch.cat(tproj_w, dim=0))
@@ -293,12 +296,18 @@ class UNetPlan(PlanBase):
                 if has_attn:
                     x = self._transformer(f"up{i}.attn{j}", x, c, h)
             if has_up:
-                up = self._buf(nb * 4 * h * h, c)
-                self._op(lambda x=x, h=h, c=c, up=up: nat.upsample2x(x, nb, h, h, c, up),
-                         tag=f"upsample:{nb * h * h}:up{i}")
-                h *= 2
-                y = self._buf(nb * h * h, c)
-                self._gemm(W.L[f"up{i}.up"], [up], [c], nb, h, h, [(0, 9)], y, stream=True)
+                lu = W.L[f"up{i}.up"]
+                y = self._buf(nb * 4 * h * h, c)
+                if lu.extra.get("up2", False):
+                    # Upsample2D in one launch: the conv reads the low-resolution tensor, phase by phase
+                    self._gemm(lu, [x], [c], nb, h, h, [(0, 4)], y, stream=True, upsample2=True)
+                    h *= 2
+                else:
+                    up = self._buf(nb * 4 * h * h, c)
+                    self._op(lambda x=x, h=h, c=c, up=up: nat.upsample2x(x, nb, h, h, c, up),
+                             tag=f"upsample:{nb * h * h}:up{i}")
+                    h *= 2
+                    self._gemm(lu, [up], [c], nb, h, h, [(0, 9)], y, stream=True)
                 x = y
         a = self._buf(nb * h * h, c)
         self._gn("norm_out", x, c, None, 0, h * h, True, a)

@@ -32,7 +32,7 @@ def test_igemm_params_struct_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_0-9]+)\s*(?:\[[A-Z_]+\])?\s*[,;]", body)
     fields = [f[0] for f in nat.IgemmParams._fields_]
-    assert fields == names and len(fields) == 46
+    assert fields == names and len(fields) == 47
 
 
 def test_product_scheduler_host_logic_matches_reference(golden_dir):
@@ -132,6 +132,34 @@ def test_weight_packing_is_a_valid_gemm_layout():
     for n, k in ((0, 0), (17, 70), (39, 191), (25, 128)):
         assert tp[n // 16, k // 64, n % 16, k % 64] == w2[n, k]
     assert tp[2, :, 8:, :].abs().sum() == 0          # rows 40..47 are padding
+
+
+def test_upsample2_phase_packing_equals_interpolate_plus_conv():
+    """pack_upsample2_conv3x3 (ldmseg_igemm_params.upsample2): the four stacked 2x2 phase matrices, applied to the
+    input pixels the kernel reads -- tap (a, b) of phase (py, px) at (y+py+a-1, x+px+b-1), zero outside --
+    reproduce F.interpolate(nearest x2) + conv3x3 (diffusers Upsample2D) at the output pixels (2y+py, 2x+px)."""
+    import torch.nn.functional as F
+    from ldmseg import _pack as pk
+    g = torch.Generator().manual_seed(1)
+    n, c, h = 24, 40, 6
+    w, x = torch.randn(n, c, 3, 3, generator=g), torch.randn(2, c, h, h, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    packed = pk.pack_upsample2_conv3x3(w)
+    npad, cp = 32, 64
+    assert packed.shape == (4 * npad, 4 * cp)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            wp = packed[(2 * py + px) * npad:(2 * py + px) * npad + n].reshape(n, 4, cp)
+            assert wp[:, :, c:].abs().sum() == 0                       # channel padding
+            acc = torch.zeros(2, n, h, h)
+            for a in range(2):
+                for b in range(2):
+                    acc += torch.einsum("bchw,nc->bnhw", xp[:, :, py + a:py + a + h, px + b:px + b + h], wp[:, 2 * a + b, :c])
+            out[:, :, py::2, px::2] = acc
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+    assert packed[n:npad].abs().sum() == 0                             # row padding of phase 0
 
 
 def test_tiling_heuristic():

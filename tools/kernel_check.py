@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_streamk", "igemm_pair", "igemm_s2", "igemm_f32stream", "igemm_lnfold",
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_streamk", "igemm_pair", "igemm_s2", "igemm_up2", "igemm_f32stream", "igemm_lnfold",
           "gn_fused", "norm", "attn_simple", "attn", "xattn", "elementwise", "sampler", "panoptic", "vae_pdl"]
 
 
@@ -447,6 +447,57 @@ def run_group(group):
                 ref = F.silu(ref)
             ref = ref.permute(0, 2, 3, 1).reshape(nb * hout * hout, cout)
             ok &= report(f"igemm conv3x3 stride 2 (TMA) {nb}x{hin}->{hout} {cin}->{cout} pad={pad} {kw}", out, ref, 1e-2)
+    elif group == "igemm_up2":
+        # nearest x2 up-sampling folded into the 3x3 convolution after it (diffusers Upsample2D): four 2x2 phase GEMMs
+        # over the input pixels against F.interpolate(nearest) + F.conv2d in fp32; (nb, hin) INPUT geometry.  The UNet's
+        # three shapes at batch 1 / 2 / 8 in every schedule the planner may pick, statistics, f32 + shadow outputs
+        for (nb, hin, cin, cout, kw) in [
+                (1, 8, 1280, 1280, {}), (1, 8, 1280, 1280, dict(split_k=7, block_n=128)),
+                (1, 16, 1280, 1280, dict(split_k=3, block_n=256, stats=True)),
+                (1, 32, 640, 640, dict(block_n=160, stats=True)), (2, 32, 640, 640, dict(pair=True, block_n=256)),
+                (1, 32, 640, 640, dict(pair=True, block_n=160, split_k=2, stats=True)),
+                (8, 16, 1280, 1280, dict(pair=True, block_n=256, stream_k=True, stats=True)),
+                (8, 32, 640, 640, dict(block_n=160, stream_k=True)), (2, 16, 192, 96, dict(act=nat.ACT_SILU, block_n=64)),
+                (2, 8, 64, 72, dict(out_f32=True, stats=True)), (3, 16, 320, 320, dict(pair=True, block_n=128, stream_k=True)),
+                (8, 8, 1280, 1280, dict(pair=True, block_n=256, stats=True))]:
+            x = rnd(nb * hin * hin, cin)
+            wt = torch.randn(cout, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
+            b = torch.randn(cout, device=dev)
+            wb = pk.to_bf16(pk.tile_pack(pk.pack_upsample2_conv3x3(wt)))
+            hout = 2 * hin
+            out_f32 = kw.get("out_f32", False)
+            out = torch.full((nb * hout * hout, cout), float("nan"), device=dev, dtype=torch.float32 if out_f32 else bf)
+            out2 = torch.full((nb * hout * hout, cout), float("nan"), device=dev, dtype=bf) if out_f32 else None
+            split, tail = kw.get("split_k", 0), kw.get("stream_k", False)
+            ws = torch.full((16 * 1024 * 1024,), float("nan"), device=dev) if (split > 1 or tail) else None
+            cnt = torch.zeros(8192, device=dev, dtype=torch.int32) if (split > 1 or tail) else None
+            st = torch.zeros(nb, cout, 2, device=dev) if kw.get("stats") else None
+            p = nat.make_igemm_params([x], [cin], nb, hin, hin, [(0, 4)], wb, cout, out, cout, bias=b,
+                                      act=kw.get("act", nat.ACT_NONE), block_n=kw.get("block_n", 0), split_k=split,
+                                      workspace=ws, counters=cnt, weight_tiled=True, pair=kw.get("pair", False),
+                                      weight_static=True, pdl=True, stats=st, stats_hw=hin * hin, out2=out2,
+                                      stream_k=tail, upsample2=True)
+            for _ in range(2):          # twice: split-K / tail counters must have re-armed themselves
+                if st is not None:
+                    st.zero_()
+                nat.igemm(p)
+            torch.cuda.synchronize()
+            xi = x.float().reshape(nb, hin, hin, cin).permute(0, 3, 1, 2)
+            ref = F.conv2d(F.interpolate(xi, scale_factor=2.0, mode="nearest"), wt.to(bf).float(), b, padding=1)
+            if kw.get("act") == nat.ACT_SILU:
+                ref = F.silu(ref)
+            ref = ref.permute(0, 2, 3, 1).reshape(nb * hout * hout, cout)
+            name = f"igemm upsample2 + conv3x3 {nb}x{hin}->{hout} {cin}->{cout} {kw}"
+            # (a phase weight is the f32 sum of up to four taps rounded to bf16 once: same error class as the taps')
+            ok &= report(name, out, ref, 1e-2 if not out_f32 else 6e-3)
+            if out2 is not None:
+                ok &= report(name + " [bf16 shadow]", out2, ref, 1e-2)
+            if st is not None:
+                o = out.float().reshape(nb, hout * hout, cout)
+                ok &= report(name + " [stats sum]", st[:, :, 0], o.sum(1), 2e-3)
+                ok &= report(name + " [stats sumsq]", st[:, :, 1], (o * o).sum(1), 2e-3)
+            if cnt is not None:
+                ok &= report(name + " [counters reset]", cnt.float(), torch.zeros_like(cnt).float(), 0.0)
     elif group == "igemm_f32stream":
         # fp32 residual stream: f32 residual in, f32 out + bf16 shadow, statistics of the f32 values
         for (nb, h, cin, cout, taps, kw) in [(2, 32, 320, 320, 9, {}), (1, 64, 320, 320, 1, {}),
