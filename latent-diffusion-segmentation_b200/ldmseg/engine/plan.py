@@ -44,6 +44,9 @@ SPLIT_CLUSTER = os.environ.get("LDMSEG_SPLIT_CLUSTER", "0") != "0"
 UP2_FOLD = os.environ.get("LDMSEG_UP2_FOLD", "1") != "0"
 
 
+# 320-wide pair tiles (csrc/igemm.cu, IgemmCfg: two N = 160 tcgen05.mma per k-step over three accumulator slots) for
+# the multi-wave N = 320 / 640 / 1280 convolutions of batches >= 4; 0 = at most 256-wide tiles
+USE_BN320 = os.environ.get("LDMSEG_BN320", "1") != "0"
 USE_TUNED = os.environ.get("LDMSEG_TUNED", "1") != "0"
 _TUNED: Optional[Dict[str, list]] = None
 
@@ -87,7 +90,8 @@ CSPLIT_EXCHANGE_CYC = 3500.0
 
 def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: bool = True,
                      allow_pair: bool = False, use_tuned: bool = True, allow_tail: bool = False,
-                     cluster_cap: Optional[Callable[[int, int], int]] = None) -> Tuple[int, int, bool, bool, bool]:
+                     cluster_cap: Optional[Callable[[int, int], int]] = None,
+                     allow_320: bool = False) -> Tuple[int, int, bool, bool, bool]:
     """Pick (block_n, split_k, pair, stream_k_tail, split_cluster) for an igemm of M x N with num_kb 64-wide K blocks.
     `cluster_cap(block_n, split)`: how many clusters of `split` CTAs the device holds at once (None: no clusters).
 
@@ -111,7 +115,9 @@ def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: b
     # (not for short K: there the epilogue bounds the kernel and coupling two CTAs' accumulator hand-over costs
     # 10-14 %, measured at K = 320)
     if allow_pair and m_tiles >= 2 and m_tiles % 2 == 0 and num_kb >= 10:
-        cands = [(bn, True) for bn in (256, 160, 128)] + cands
+        # 320-wide pair tiles (two N = 160 MMAs per k-step sharing the staged A rows; whole tiles or stream-K tail
+        # only, not GEGLU): a third less shared-memory traffic per multiply-add than 160-wide tiles
+        cands = [(bn, True) for bn in ((320, 256, 160, 128) if allow_320 and n >= 320 else (256, 160, 128))] + cands
     for bn, pair in cands:
         tiles = m_tiles * ((n + bn - 1) // bn)
         t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + bn))
@@ -125,10 +131,13 @@ def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: b
             # multi-wave launches, measured per k-block at batch 8 under the power cap (pairs:
             # profiles/r02_ablate_unet_b8_streamk*.log; single CTAs from the pair / single ratios of
             # profiles/r01_bench_ingest_v11.log): the fit above is 7 % low at bn 160 and 15 % high at bn 256
-            t_kb = {128: 545.0, 160: 620.0, 256: 665.0}[bn] if pair else {128: 580.0, 160: 660.0, 256: 719.0}[bn]
+            # (320: tools/bench_bn320.py, profiles/r02_bench_bn320.log -- 834 cycles against 2 x 604 for the same
+            # columns as two 160-wide tiles)
+            t_kb = ({128: 545.0, 160: 620.0, 256: 665.0, 320: 834.0}[bn] if pair
+                    else {128: 580.0, 160: 660.0, 256: 719.0}[bn])
         chunks = bn / 32.0
         splits = [1]
-        if allow_split and tiles < sms:
+        if allow_split and tiles < sms and bn != 320:
             s = 2
             while tiles * s <= sms and num_kb // s >= 4 and s <= 16:
                 splits.append(s)
@@ -299,13 +308,14 @@ class PlanBase:
         tail_ok = STREAM_K and allow_split and tiled and act != nat.ACT_GEGLU
         geglu = act == nat.ACT_GEGLU
         cap = (lambda bn_, s_: nat.max_split_clusters(bn_, geglu, s_)) if SPLIT_CLUSTER and allow_split else None
+        allow_320 = USE_BN320 and not geglu
         bn, split, pair, stream_k, split_cluster = choose_tiling_ex(
             m, layer.n, num_kb, allow_split=allow_split, allow_pair=allow_pair, allow_tail=tail_ok,
-            cluster_cap=cap)
+            cluster_cap=cap, allow_320=allow_320)
         tiles = ((m + 127) // 128) * ((layer.n + bn - 1) // bn)
         if split > 1 and not split_cluster and tiles * split * 128 * bn > self.ws.numel():
             bn, split, pair, stream_k, split_cluster = choose_tiling_ex(
-                m, layer.n, num_kb, allow_split=False, allow_pair=allow_pair, allow_tail=False)
+                m, layer.n, num_kb, allow_split=False, allow_pair=allow_pair, allow_tail=False, allow_320=allow_320)
         out_main, out2 = out, None
         if stream and self.resid_f32 and out.dtype == torch.bfloat16:
             f = self._buf(out.shape[0], out.shape[1], torch.float32)

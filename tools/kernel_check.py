@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "latent-diffusion-segmentation_b200"))
 
-GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_streamk", "igemm_pair", "igemm_s2", "igemm_up2", "igemm_f32stream", "igemm_lnfold",
+GROUPS = ["simple", "igemm_plain", "igemm_conv", "igemm_epi", "igemm_splitk", "igemm_streamk", "igemm_pair", "igemm_bn320", "igemm_s2", "igemm_up2", "igemm_f32stream", "igemm_lnfold",
           "gn_fused", "norm", "attn_simple", "attn", "xattn", "elementwise", "sampler", "panoptic", "vae_pdl"]
 
 
@@ -279,6 +279,32 @@ def run_group(group):
                   block_n=160, split_k=3, stats=True, pair=True)
         conv_case("pair conv3x3 1x64x64 320->4 f32 bn128 (conv_out)", 1, 64, 64, 320, 4, out_f32=True, block_n=128,
                   pair=True)
+    elif group == "igemm_bn320":
+        # 320-wide pair tiles: two N = 160 tcgen05.mma per k-step over three accumulator slots (ring), the first k-blocks'
+        # first-half MMAs issued ahead of the second-half ones
+        conv_case("bn320 pair linear 4096x320->640 (1 tile per pair)", 1, 1, 4096, 320, 640, taps=1, block_n=320, pair=True)
+        conv_case("bn320 pair linear 256x128->320 (k shorter than the run-ahead)", 1, 1, 256, 128, 320, taps=1,
+                  block_n=320, pair=True)
+        conv_case("bn320 pair conv3x3 1x64x64 320->320 +res +rowbias +stats", 1, 64, 64, 320, 320, block_n=320,
+                  residual=True, rowbias=True, stats=True, pair=True)
+        conv_case("bn320 pair conv3x3 8x64x64 320->320 (128 pair tiles: 2 waves) +res +rowbias +stats pdl", 8, 64, 64,
+                  320, 320, block_n=320, residual=True, rowbias=True, stats=True, pair=True, pdl=True)
+        conv_case("bn320 pair linear 40960x320->640 (320 pair tiles: 5 waves: every slot order) silu", 1, 1, 40960, 320,
+                  640, taps=1, block_n=320, pair=True, act=nat.ACT_SILU)
+        conv_case("bn320 pair conv3x3 8x32x32 640->640 (64 pair tiles) f32 +stats", 8, 32, 32, 640, 640, block_n=320,
+                  out_f32=True, stats=True, pair=True)
+        conv_case("bn320 pair conv3x3 dual + 1x1 shortcut 2x32x32 -> 640", 2, 32, 32, 640, 640, extra_src=320,
+                  shortcut=True, block_n=320, pair=True)
+        conv_case("bn320 pair linear 384x640->1280 (odd tile count, phantom) +stats", 1, 1, 384, 640, 1280, taps=1,
+                  block_n=320, pair=True, stats=True)
+        conv_case("bn320 pair linear 1024x640->400 (ragged N: second half partly past N)", 1, 1, 1024, 640, 400, taps=1,
+                  block_n=320, pair=True)
+        conv_case("bn320 streamk pair conv3x3 8x64x64 320->320 (128 pair tiles: 1 wave + 54) +res +stats", 8, 64, 64,
+                  320, 320, block_n=320, residual=True, stats=True, pair=True, stream_k=True)
+        conv_case("bn320 streamk pair conv3x3 8x16x16 1280->1280 (32 pair tiles, all tail) +rowbias", 8, 16, 16, 1280,
+                  1280, block_n=320, rowbias=True, pair=True, stream_k=True)
+        conv_case("bn320 streamk pair conv3x3 8x32x32 960->640 dual (64 pair tiles, all tail) pdl", 8, 32, 32, 640, 640,
+                  extra_src=320, block_n=320, pair=True, stream_k=True, pdl=True)
     elif group == "norm":
         for (nb, hw, c0, c1) in [(1, 4096, 320, 0), (2, 1024, 640, 320), (1, 256, 1280, 640),
                                  (2, 64, 1280, 1280), (1, 65536, 256, 0)]:
@@ -459,7 +485,9 @@ def run_group(group):
                 (8, 16, 1280, 1280, dict(pair=True, block_n=256, stream_k=True, stats=True)),
                 (8, 32, 640, 640, dict(block_n=160, stream_k=True)), (2, 16, 192, 96, dict(act=nat.ACT_SILU, block_n=64)),
                 (2, 8, 64, 72, dict(out_f32=True, stats=True)), (3, 16, 320, 320, dict(pair=True, block_n=128, stream_k=True)),
-                (8, 8, 1280, 1280, dict(pair=True, block_n=256, stats=True))]:
+                (8, 8, 1280, 1280, dict(pair=True, block_n=256, stats=True)),
+                (8, 32, 640, 640, dict(pair=True, block_n=320, stats=True)),
+                (4, 16, 1280, 1280, dict(pair=True, block_n=320, stream_k=True))]:
             x = rnd(nb * hin * hin, cin)
             wt = torch.randn(cout, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
             b = torch.randn(cout, device=dev)
