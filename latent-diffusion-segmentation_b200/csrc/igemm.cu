@@ -34,8 +34,19 @@ constexpr int BK = 64;
 // and two warps per scheduler left it latency-bound (ncu at batch 8: issue 52 %, tensor 29 %; 87 -> 64 us at
 // M = 32768, K = 320, N = 2560).  The plain epilogue gains nothing from 16 warps (measured: it is bound by the
 // rate of its 32-byte sector stores at wide N, not by latency) and the batch-1 forward loses 0.7 %.
-__host__ __device__ constexpr int igemm_epi_warps(bool geglu, bool split) { return (geglu && !split) ? 16 : 8; }
-__host__ __device__ constexpr int igemm_threads(bool geglu, bool split) { return 64 + 32 * igemm_epi_warps(geglu, split); }
+// The 320-wide pair tile: its accumulator slots are single-buffered halves, so the time the epilogue needs to drain a
+// half stalls the next tile's MMAs (and the last tile's epilogue is exposed in full: 17 of 57 us at N = K = 320, batch
+// 8, profiles/r02_bench_bn320_stages.log).  16 epilogue warps (-DLDMSEG_BN320_EPI_WARPS=16) were measured and do not
+// help (57.9 against 56.1 us, profiles/r02_bench_bn320_epi16.log): like the plain epilogue above it is not latency-bound.
+#ifndef LDMSEG_BN320_EPI_WARPS
+#define LDMSEG_BN320_EPI_WARPS 8
+#endif
+__host__ __device__ constexpr int igemm_epi_warps(bool geglu, bool split, int bn = 0) {
+  return bn == 320 ? LDMSEG_BN320_EPI_WARPS : (geglu && !split) ? 16 : 8;
+}
+__host__ __device__ constexpr int igemm_threads(bool geglu, bool split, int bn = 0) {
+  return 64 + 32 * igemm_epi_warps(geglu, split, bn);
+}
 constexpr int kABytes = BM * BK * 2;  // 16 KB per stage
 
 struct alignas(64) IgemmKParams {
@@ -717,13 +728,13 @@ __device__ __forceinline__ int tail_plan(int tail_full_tiles, int tail_tiles, in
 }
 
 template <int BN, bool GEGLU, bool SPLIT, bool PAIR, bool TAIL = false, bool CSPLIT = false>
-__global__ void __launch_bounds__(igemm_threads(GEGLU, SPLIT), 1)
+__global__ void __launch_bounds__(igemm_threads(GEGLU, SPLIT, BN), 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
   static_assert(!(TAIL && (SPLIT || GEGLU)), "the stream-K tail replaces split-K; it is not built for GEGLU");
   static_assert(!CSPLIT || (SPLIT && !PAIR && !TAIL), "the cluster exchange is a form of split-K for single CTAs");
   static_assert(BN != 320 || (PAIR && !SPLIT && !GEGLU), "the 320-wide tile: CTA pairs, whole tiles or the stream-K tail");
   using Cfg = IgemmCfg<BN, PAIR>;
-  constexpr int kEpiWarps = igemm_epi_warps(GEGLU, SPLIT);
+  constexpr int kEpiWarps = igemm_epi_warps(GEGLU, SPLIT, BN);
   constexpr int kEpiThreads = kEpiWarps * 32;
   constexpr int NH = kEpiWarps / 4;
   constexpr int kStages = Cfg::kStages;
@@ -1087,8 +1098,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     };
     // One tile's accumulator through epilogue_warp<MODE> and back to the MMA issuer.  320-wide tiles: the two 160-wide
     // halves one after the other (ring slots 2 it, 2 it + 1 mod 3), each slot released as soon as it is drained -- the
-    // next tile's second half is waiting for the FIRST one; the warps of a quadrant swap their chunk parity for the
-    // second half (5 chunks per half: 3 + 2 each way).
+    // next tile's second half is waiting for the FIRST one; the warps of a quadrant rotate their chunk residue for the
+    // second half (5 chunks per half dealt to NH warps: whoever took two of the first half takes one of the second).
     auto run_epilogue = [&](auto mode, int it, uint32_t t_row, float* ws_tile, int sidx, int m_base, int n0, int q,
                             int half, float2 ln_rs) {
       constexpr int MODE = decltype(mode)::value;
@@ -1103,7 +1114,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
           epilogue_warp<Cfg::kSubN, GEGLU, MODE, NH>(
               ea, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * Cfg::kSubN,
               ws_tile != nullptr ? ws_tile + j * (BM * Cfg::kSubN) : nullptr, sidx, m_base, n0 + j * Cfg::kSubN, q,
-              half ^ j, lane, ln_rs, BM * BN);
+              (half + j * (NH / 2)) % NH, lane, ln_rs, BM * BN);
           tc_fence_before();
           release_acc(s);
         }
@@ -1203,7 +1214,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         if (split == 1) {
           // a piece that ends inside the tile: publish the partial accumulator
           run_epilogue(ModePartial{}, it, t_row, ws_tile, slot, m_base, n0, q, half, ln_rs);
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread's stores before thread 0's release
+          asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");   // every thread's stores before thread 0's release
           if (et == 0) {
             int seen;
             asm volatile("atom.release.gpu.global.add.s32 %0, [%1], 1;" : "=r"(seen) : "l"(p.counters + tt) : "memory");
@@ -1218,9 +1229,9 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
               if (++spins > (1u << 26)) __trap();
             } while (seen < slot);
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
           run_epilogue(ModeDirectAdd{}, it, t_row, ws_tile, slot, m_base, n0, q, half, ln_rs);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
           if (et == 0) p.counters[tt] = 0;   // re-armed for the next launch (all `slot` arrivals were consumed)
         } else {
           run_epilogue(ModeDirect{}, it, t_row, nullptr, 0, m_base, n0, q, half, ln_rs);
@@ -1476,7 +1487,7 @@ static int launch_igemm_v(const IgemmKParams& kp, int grid, cudaStream_t stream,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(igemm_threads(GEGLU, SPLIT));
+  cfg.blockDim = dim3(igemm_threads(GEGLU, SPLIT, BN));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

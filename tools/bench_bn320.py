@@ -14,15 +14,15 @@ from ldmseg import _native as nat  # noqa: E402
 from ldmseg import _pack as pk  # noqa: E402
 
 
-def run_case(nb, h, cin, n, bn, tail, iters=20):
+def run_case(nb, h, cin, n, bn, tail, iters=20, residual=True, stats=True, out_f32=False):
     dev = "cuda"
     m = nb * h * h
     x = torch.randn(m, cin, device=dev).to(torch.bfloat16)
     wt = pk.to_bf16(pk.tile_pack(pk.pack_conv3x3(torch.randn(n, cin, 3, 3, device=dev) * 0.02)))
-    out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(m, n, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
     bias = torch.randn(n, device=dev)
-    res = torch.randn(m, n, device=dev).to(torch.bfloat16)
-    st = torch.zeros(nb, n, 2, device=dev)
+    res = torch.randn(m, n, device=dev).to(torch.bfloat16) if residual else None
+    st = torch.zeros(nb, n, 2, device=dev) if stats else None
     ws = torch.zeros(16 * 1024 * 1024, device=dev)
     cnt = torch.zeros(8192, device=dev, dtype=torch.int32)
     p = nat.make_igemm_params([x], [cin], nb, h, h, [(0, 9)], wt, n, out, n, bias=bias, residual=res, res_ld=n,
@@ -49,19 +49,27 @@ def run_case(nb, h, cin, n, bn, tail, iters=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", nargs="+", type=int, default=[8, 4, 2])
+    ap.add_argument("--profile", nargs=5, type=int, default=None, help="nb h cin n bn")
     ap.add_argument("--stages", action="store_true",
                     help="where the time of one launch goes: the same case with the epilogue dropped, without fused "
                          "statistics, without operand loads (igemm debug switches; results are garbage)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
+    if args.profile:   # a few eager launches of one case for an ncu capture (ncu -k regex:igemm -s 3 -c 1)
+        nb, h, cin, n, bn = args.profile
+        run_case(nb, h, cin, n, bn, False, iters=2)
+        return
     if args.stages:
         for (nb, h, cin, n) in [(8, 64, 320, 320), (8, 64, 960, 320), (8, 32, 640, 640)]:
-            for bn, tail in ((320, False), (160, True)):
+            for bn, tail in ((320, False), (160, False)):
                 line = f"nb={nb} {h}x{h} {cin}->{n} bn{bn}{'t' if tail else ''}:"
-                for name, flags in (("full", 0), ("no epilogue", 32), ("no stats", 128), ("no loads after kb0", 24),
-                                    ("no loads, no epilogue", 56)):
-                    nat.load().ldmseg_set_debug(flags)
-                    line += f"  {name} {run_case(nb, h, cin, n, bn, tail):6.1f}"
+                for name, kw in (("full", {}), ("no residual", dict(residual=False)), ("no stats", dict(stats=False)),
+                                 ("bias only", dict(residual=False, stats=False)),
+                                 ("bias only, f32 out", dict(residual=False, stats=False, out_f32=True)),
+                                 ("f32 out", dict(out_f32=True))):
+                    line += f"  {name} {run_case(nb, h, cin, n, bn, tail, **kw):6.1f}"
+                nat.load().ldmseg_set_debug(32)
+                line += f"  no epilogue {run_case(nb, h, cin, n, bn, tail):6.1f}"
                 nat.load().ldmseg_set_debug(0)
                 print(line, flush=True)
         return
