@@ -173,6 +173,18 @@ def test_tiling_heuristic():
     assert split == 1
     bn, split, pair = choose_tiling(8 * 4096, 320, 45, allow_pair=True)   # ingest-bound conv: pair halves the B staging
     assert pair and bn in (128, 160, 256) and split == 1
+    # 320-wide pair tiles (two N = 160 MMAs per k-step): the multi-wave N = 320 / 640 convolutions of batch 8, measured
+    # in profiles/r02_bench_bn320.log; never with split-K, never unless the caller allows them (GEGLU launches do not)
+    from ldmseg.engine.plan import choose_tiling_ex
+    for (m, n, kb) in ((8 * 4096, 320, 45), (8 * 4096, 320, 135), (8 * 1024, 640, 90), (8 * 1024, 640, 270),
+                       (4 * 4096, 320, 90)):
+        bn, split, pair, tail, clus = choose_tiling_ex(m, n, kb, allow_pair=True, allow_tail=True, allow_320=True)
+        assert (bn, split, pair, clus) == (320, 1, True, False), (m, n, kb, bn, split, pair, tail)
+        assert choose_tiling_ex(m, n, kb, allow_pair=True, allow_tail=True)[0] != 320
+    for (m, n, kb) in ((8 * 256, 1280, 180), (2 * 4096, 320, 45), (4096, 320, 45), (64, 1280, 180)):
+        bn, split, pair, tail, clus = choose_tiling_ex(m, n, kb, allow_pair=True, allow_tail=True, allow_320=True)
+        assert bn != 320 or (pair and split == 1), (m, n, kb, bn, split, pair)
+    assert choose_tiling_ex(8 * 256, 1280, 180, allow_pair=True, allow_tail=True, allow_320=True)[0] == 256
 
 
 def test_tuned_tiling_table_is_legal():
