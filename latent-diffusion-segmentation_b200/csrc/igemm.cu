@@ -2,8 +2,9 @@
 //
 // One kernel covers every contraction of the UNet / VAE hot path that is not attention:
 // conv3x3 (9 shifted TMA box loads of the channel-last activation, zero padding by TMA
-// out-of-bounds fill), conv1x1 / linear (1 tap), concat-free skip connections and the fused 1x1
-// shortcut (several K segments accumulating into one TMEM tile).
+// out-of-bounds fill), stride-2 conv3x3 (TMA traversal stride), nearest x2 up-sampling + conv3x3 (four 2x2 phase
+// GEMMs over the low-resolution tensor, see IgemmKParams::up2), conv1x1 / linear (1 tap), concat-free skip
+// connections and the fused 1x1 shortcut (several K segments accumulating into one TMEM tile).
 //
 // Replaces F.conv2d / F.linear inside diffusers' ResnetBlock2D / Transformer2DModel / Attention /
 // FeedForward / Downsample2D / Upsample2D as called from /root/reference/ldmseg/models/unet.py:357,
@@ -17,7 +18,8 @@
 // (tmem_full/tmem_empty) between MMA and epilogue so tile i's epilogue overlaps tile i+1's MMAs.
 //
 // Tile: BLOCK_M = 128 output pixels x BN output channels, BLOCK_K = 64 (one 128-byte swizzle row).
-// PAIR variant: two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2) -- see IgemmCfg.
+// PAIR variant: two CTAs of a cluster form one 256 x BN tile (tcgen05 cta_group::2), BN up to 320 (two N = 160
+// instructions per k-step over three accumulator slots) -- see IgemmCfg.
 #include "common.h"
 #include <cstdlib>
 #include <cstring>
