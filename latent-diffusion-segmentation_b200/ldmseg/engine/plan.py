@@ -117,7 +117,11 @@ def choose_tiling_ex(m: int, n: int, num_kb: int, sms: int = SMS, allow_split: b
     if allow_pair and m_tiles >= 2 and m_tiles % 2 == 0 and num_kb >= 10:
         # 320-wide pair tiles (two N = 160 MMAs per k-step sharing the staged A rows; whole tiles or stream-K tail
         # only, not GEGLU): a third less shared-memory traffic per multiply-add than 160-wide tiles
-        cands = [(bn, True) for bn in ((320, 256, 160, 128) if allow_320 and n >= 320 else (256, 160, 128))] + cands
+        # -- from ~32 k-blocks on: per layer in the batch-8 forward (profiles/r02_ablate_unet_b8_i.log against
+        # r02_ablate_unet_b8_h.log) every convolution and the K = 2560 feed-forward output gained 6-44 us, the K = 640 /
+        # 1280 projections (10 / 20 k-blocks, epilogue-bound) lost 0.6-2.4 us each
+        wide = allow_320 and n >= 320 and num_kb >= 32
+        cands = [(bn, True) for bn in ((320, 256, 160, 128) if wide else (256, 160, 128))] + cands
     for bn, pair in cands:
         tiles = m_tiles * ((n + bn - 1) // bn)
         t_kb = max(2.0 * bn, CYC_PER_TMA_ROW * (128 + bn))

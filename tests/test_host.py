@@ -185,6 +185,9 @@ def test_tiling_heuristic():
         bn, split, pair, tail, clus = choose_tiling_ex(m, n, kb, allow_pair=True, allow_tail=True, allow_320=True)
         assert bn != 320 or (pair and split == 1), (m, n, kb, bn, split, pair)
     assert choose_tiling_ex(8 * 256, 1280, 180, allow_pair=True, allow_tail=True, allow_320=True)[0] == 256
+    # short-K projections (10 / 20 k-blocks) are epilogue-bound and lose with the wide tile: measured, kept narrow
+    for (m, n, kb) in ((8 * 1024, 640, 10), (8 * 4096, 320, 20), (8 * 1024, 1920, 10)):
+        assert choose_tiling_ex(m, n, kb, allow_pair=True, allow_tail=True, allow_320=True)[0] != 320
 
 
 def test_tuned_tiling_table_is_legal():
