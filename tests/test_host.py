@@ -160,6 +160,11 @@ def test_upsample2_phase_packing_equals_interpolate_plus_conv():
             out[:, :, py::2, px::2] = acc
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
     assert packed[n:npad].abs().sum() == 0                             # row padding of phase 0
+    # block-tiled as the TMA weight map reads it: phase p starts at 16-row block p * ceil(N / 16) (IgemmKParams::up_nblk)
+    tp = pk.tile_pack(packed)
+    assert tp.shape == (4 * npad // 16, 4 * cp // 64, 16, 64)
+    for ph in range(4):
+        assert torch.equal(tp[ph * (npad // 16), 1, 3, :c], packed[ph * npad + 3, cp:cp + c])   # row 3, tap 1
 
 
 def test_tiling_heuristic():
