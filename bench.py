@@ -364,7 +364,11 @@ def kernel_roofline(plan, peaks):
     achieved = flops / (ig_ms / 1e3) / 1e12
     # dram bytes per launch of this kernel from the committed ncu --set full capture (tools/make_traffic_json.py)
     traffic, traffic_src = None, None
+    # (one file per captured batch: the batch-8 capture holds the 320-wide pair tiles)
     tpath = os.path.join(ROOT, "profiles", "igemm_dram_traffic.json")
+    tpath8 = os.path.join(ROOT, "profiles", "igemm_dram_traffic_b8.json")
+    if getattr(plan, "nb", 1) >= 8 and os.path.exists(tpath8):
+        tpath = tpath8
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)

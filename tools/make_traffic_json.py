@@ -1,6 +1,6 @@
 """profiles/igemm_dram_traffic.json from an ncu --set full summary (tools/ncu_summary.py output): the average
 dram__bytes_read.sum + dram__bytes_write.sum per captured igemm launch.  bench.py reports it as roofline.traffic.
-Usage: python tools/make_traffic_json.py profiles/r01_ncu_igemm_full_b1_vNN.txt"""
+Usage: python tools/make_traffic_json.py profiles/r02_ncu_igemm_full_b1.txt [igemm_dram_traffic_b8.json]"""
 import json
 import os
 import sys
@@ -19,7 +19,8 @@ def main():
     out = {"traffic": round(sum(tot) / len(tot)), "unit": "bytes per launch (dram read + write, mean of the captured launches)",
            "launches_captured": len(tot), "mean_duration_us_under_ncu": round(sum(durs) / len(durs), 2),
            "source": os.path.relpath(path, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))}
-    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "igemm_dram_traffic.json")
+    name = sys.argv[2] if len(sys.argv) > 2 else "igemm_dram_traffic.json"   # igemm_dram_traffic_b8.json for batch 8
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", name)
     with open(dst, "w") as f:
         json.dump(out, f)
     print(out)
